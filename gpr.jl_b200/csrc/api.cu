@@ -1,0 +1,569 @@
+// C ABI of libgprb200 (include/gprb200.h): handle management and the host-side orchestration of the
+// evaluation pipeline  assembly -> blocked Cholesky -> solves/mll -> inverse -> fused gradient.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <new>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gprb {
+
+static thread_local std::string g_err = "";
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")";
+  return e == cudaErrorMemoryAllocation ? GPRB_ERR_NOMEM : GPRB_ERR_CUDA;
+}
+
+__global__ void k_reset_jitter(double* jitter, const int32_t* list, int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) jitter[list[k]] = 0.0;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+  return 0;
+}
+
+static void free_batch(gprb_batch* b) {
+  if (!b) return;
+  cudaFree(b->Xptr); cudaFree(b->Xtptr); cudaFree(b->ymm); cudaFree(b->theta); cudaFree(b->A); cudaFree(b->Lm);
+  cudaFree(b->Dinv); cudaFree(b->DinvT); cudaFree(b->alpha); cudaFree(b->zbuf); cudaFree(b->jitter);
+  cudaFree(b->logdet_part); cudaFree(b->fail); cudaFree(b->mll); cudaFree(b->grad);
+  cudaFree(b->grad_part); cudaFree(b->list);
+  if (b->list_host) cudaFreeHost(b->list_host);
+  if (b->fail_host) cudaFreeHost(b->fail_host);
+  if (b->stage_host) cudaFreeHost(b->stage_host);
+  for (int s = 0; s < 4; ++s) {
+    if (b->stream[s]) cudaStreamDestroy(b->stream[s]);
+    if (b->join[s]) cudaEventDestroy(b->join[s]);
+  }
+  for (int s = 0; s < 8; ++s)
+    if (b->ev[s]) cudaEventDestroy(b->ev[s]);
+  delete b;
+}
+
+// Enqueue one full evaluation of the GPs in list[off .. off+count) on `st`.
+static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, cudaStream_t st, bool prof) {
+  if (count <= 0) return 0;
+  const int32_t* list = b->list + off;
+  const int J = b->J;
+  const int64_t ms = b->npad * b->npad, dstride = (int64_t)J * NB * NB;
+  int rc;
+  int64_t& launches = b->ctx->launches;
+  if (prof) cudaEventRecord(b->ev[0], st);
+  AssembleArgs aa{b->Xtptr, b->theta, b->jitter, b->A, b->fail, list, ms, (int)b->n, (int)b->npad, b->d, J, b->kind};
+  if ((rc = launch_assemble(aa, count, st))) return rc;
+  ++launches;
+  if (prof) cudaEventRecord(b->ev[1], st);
+  GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG};
+  DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0};
+  for (int j = 0; j < J; ++j) {
+    ga.step = j; ga.mode = GEMM_CHOL_DIAG;
+    if ((rc = launch_tile_gemm(ga, 1, count, st))) return rc;
+    da.step = j;
+    if ((rc = launch_diag_factor(da, count, st))) return rc;
+    launches += 2;
+    if (j + 1 < J) {
+      ga.mode = GEMM_CHOL_COL;
+      if ((rc = launch_tile_gemm(ga, J - 1 - j, count, st))) return rc;
+      ++launches;
+    }
+  }
+  if (prof) cudaEventRecord(b->ev[2], st);
+  SolveArgs sa{b->Lm, b->Dinv, b->ymm, b->logdet_part, b->fail, b->zbuf, b->alpha, b->mll, list, ms, dstride,
+               (int)b->n, (int)b->npad, J};
+  if ((rc = launch_solve(sa, count, st))) return rc;
+  ++launches;
+  if (prof) cudaEventRecord(b->ev[3], st);
+  if (with_grad) {
+    ga.Cin = nullptr;
+    for (int i = 1; i < J; ++i) {
+      ga.step = i; ga.mode = GEMM_TRTRI_ROW; ga.Cout = b->Lm;
+      if ((rc = launch_tile_gemm(ga, i, count, st))) return rc;
+      ++launches;
+    }
+    ga.mode = GEMM_LAUUM; ga.step = 0; ga.Cout = b->A;
+    if ((rc = launch_tile_gemm(ga, J * (J + 1) / 2, count, st))) return rc;
+    ++launches;
+    if (prof) cudaEventRecord(b->ev[4], st);
+    GradArgs gr{b->Xtptr, b->theta, b->A, b->alpha, b->grad_part, b->grad, b->fail, list, ms,
+                (int)b->n, (int)b->npad, b->d, J, b->kind};
+    if ((rc = launch_grad(gr, count, st))) return rc;
+    launches += 2;
+    if (prof) cudaEventRecord(b->ev[5], st);
+  }
+  return 0;
+}
+
+// Run the pipeline over the first `count` entries of b->list, split over the batch's streams so the serial
+// diagonal-block kernels of one group overlap the DMMA tiles of another.  Joins everything on stream[0].
+static int run_pipeline(gprb_batch* b, int count, bool with_grad) {
+  int rc;
+  if (b->profiling || count < 8 || b->nstreams == 1) {
+    if ((rc = enqueue_pipeline(b, 0, count, with_grad, b->stream[0], b->profiling))) return rc;
+    if (b->profiling) {
+      GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+      float ms = 0.f;
+      const int last = with_grad ? 5 : 3;
+      for (int s = 0; s < 5; ++s) b->stage_ms[s] = 0.0;
+      for (int s = 0; s < last; ++s) {
+        GPRB_CUDA(cudaEventElapsedTime(&ms, b->ev[s], b->ev[s + 1]));
+        b->stage_ms[s] = ms;
+      }
+      GPRB_CUDA(cudaEventElapsedTime(&ms, b->ev[0], b->ev[last]));
+      b->stage_ms[5] = ms;
+    }
+    return 0;
+  }
+  const int S = b->nstreams;
+  GPRB_CUDA(cudaEventRecord(b->join[0], b->stream[0]));
+  for (int s = 0; s < S; ++s) {
+    const int lo = (int)((int64_t)count * s / S), hi = (int)((int64_t)count * (s + 1) / S);
+    if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(b->stream[s], b->join[0], 0));
+    if ((rc = enqueue_pipeline(b, lo, hi - lo, with_grad, b->stream[s], false))) return rc;
+    if (s > 0) {
+      GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
+      GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
+    }
+  }
+  return 0;
+}
+
+static int upload_list(gprb_batch* b, int count) {
+  GPRB_CUDA(cudaMemcpyAsync(b->list, b->list_host, sizeof(int32_t) * count, cudaMemcpyHostToDevice, b->stream[0]));
+  return 0;
+}
+
+// Shared tail of gprb_eval / gprb_eval_device: pipeline + make_posdef! retry loop.  list_host[0..count) holds the
+// active GPs.  On return info_host (pinned fail_host reused) holds per-GP info for ALL B (inactive untouched = 0).
+static int evaluate_active(gprb_batch* b, int count, bool with_grad, std::vector<int32_t>& info) {
+  int rc;
+  info.assign(b->B, 0);
+  if (count == 0) return 0;
+  if ((rc = upload_list(b, count))) return rc;
+  k_reset_jitter<<<(count + 127) / 128, 128, 0, b->stream[0]>>>(b->jitter, b->list, count);
+  GPRB_CUDA(cudaGetLastError());
+  if ((rc = run_pipeline(b, count, with_grad))) return rc;
+  std::vector<int32_t> tries(b->B, 0);
+  for (int attempt = 0;; ++attempt) {
+    GPRB_CUDA(cudaMemcpyAsync(b->fail_host, b->fail, sizeof(int32_t) * b->B, cudaMemcpyDeviceToHost, b->stream[0]));
+    GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+    // list_host still holds the GPs evaluated in the last pass (first `count` entries)
+    int nretry = 0;
+    std::vector<int32_t> again;
+    for (int k = 0; k < count; ++k) {
+      const int gp = b->list_host[k];
+      const int f = b->fail_host[gp];
+      if (f == 0) info[gp] = tries[gp];
+      else if (f < 0) info[gp] = -2;
+      else if (tries[gp] >= MAX_JITTER) info[gp] = -1;
+      else { tries[gp]++; again.push_back(gp); ++nretry; continue; }
+      b->state_ok[gp] = info[gp] >= 0;
+      b->inv_ok[gp] = with_grad && info[gp] >= 0;
+    }
+    if (nretry == 0) break;
+    for (int k = 0; k < nretry; ++k) b->list_host[k] = again[k];
+    count = nretry;
+    if ((rc = upload_list(b, count))) return rc;
+    if ((rc = launch_add_jitter(b->theta, b->jitter, b->list, b->d, count, b->stream[0]))) return rc;
+    if ((rc = run_pipeline(b, count, with_grad))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace gprb
+
+using namespace gprb;
+
+extern "C" {
+
+int gprb_version(void) { return 100; }
+const char* gprb_last_error(void) { return g_err.c_str(); }
+
+int gprb_init(gprb_ctx** out, int device) {
+  GPRB_REQUIRE(out != nullptr, "gprb_init: ctx out-pointer is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("gprb_init: no CUDA device visible - libgprb200 has no CPU fallback");
+    return GPRB_ERR_NODEVICE;
+  }
+  GPRB_REQUIRE(device >= 0 && device < ndev, "gprb_init: device index out of range");
+  cudaDeviceProp prop;
+  GPRB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("gprb_init: device '") + prop.name + "' is not sm_100 (B200); the library is built for sm_100a only");
+    return GPRB_ERR_NODEVICE;
+  }
+  GPRB_CUDA(cudaSetDevice(device));
+  gprb_ctx* c = new (std::nothrow) gprb_ctx();
+  GPRB_REQUIRE(c != nullptr, "gprb_init: out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  c->clock_khz = khz;
+  c->l2_bytes = prop.l2CacheSize;
+  *out = c;
+  return GPRB_OK;
+}
+
+int gprb_destroy(gprb_ctx* ctx) {
+  delete ctx;
+  return GPRB_OK;
+}
+
+int gprb_device_info(gprb_ctx* ctx, int64_t out[4]) {
+  GPRB_REQUIRE(ctx && out, "gprb_device_info: NULL argument");
+  GPRB_CUDA(cudaSetDevice(ctx->device));
+  size_t fr = 0, tot = 0;
+  GPRB_CUDA(cudaMemGetInfo(&fr, &tot));
+  out[0] = ctx->sm_count; out[1] = ctx->clock_khz; out[2] = ctx->l2_bytes; out[3] = (int64_t)fr;
+  return GPRB_OK;
+}
+
+int64_t gprb_launch_count(gprb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+static int dataset_upload(gprb_dataset* ds, const double* X, int64_t ldx) {
+  GPRB_CUDA(cudaSetDevice(ds->ctx->device));
+  GPRB_CUDA(cudaMemcpy2D(ds->X, sizeof(double) * ds->d, X, sizeof(double) * ldx, sizeof(double) * ds->d, ds->n,
+                         cudaMemcpyHostToDevice));
+  int rc = launch_transpose_inputs(ds->X, ds->Xt, (int)ds->n, (int)ds->npad, ds->d, 0);
+  if (rc) return rc;
+  ds->ctx->launches++;
+  GPRB_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+int gprb_dataset_create(gprb_ctx* ctx, int64_t n, int32_t d, const double* X, int64_t ldx, gprb_dataset** out) {
+  GPRB_REQUIRE(ctx && X && out, "gprb_dataset_create: NULL argument");
+  *out = nullptr;
+  GPRB_REQUIRE(n >= 1 && n <= (1 << 20), "gprb_dataset_create: n out of range");
+  GPRB_REQUIRE(d >= 1 && d <= MAX_D, "gprb_dataset_create: d must be in 1..64");
+  GPRB_REQUIRE(ldx >= d, "gprb_dataset_create: ldx < d");
+  GPRB_CUDA(cudaSetDevice(ctx->device));
+  gprb_dataset* ds = new (std::nothrow) gprb_dataset();
+  GPRB_REQUIRE(ds != nullptr, "gprb_dataset_create: out of host memory");
+  ds->ctx = ctx; ds->n = n; ds->d = d;
+  ds->npad = (n + NB - 1) / NB * NB;
+  int rc;
+  if ((rc = dev_alloc(&ds->X, (size_t)n * d)) || (rc = dev_alloc(&ds->Xt, (size_t)ds->npad * d)) ||
+      (rc = dataset_upload(ds, X, ldx))) {
+    cudaFree(ds->X); cudaFree(ds->Xt); delete ds;
+    return rc;
+  }
+  *out = ds;
+  return GPRB_OK;
+}
+
+int gprb_dataset_update(gprb_dataset* ds, const double* X, int64_t ldx) {
+  GPRB_REQUIRE(ds && X, "gprb_dataset_update: NULL argument");
+  GPRB_REQUIRE(ldx >= ds->d, "gprb_dataset_update: ldx < d");
+  return dataset_upload(ds, X, ldx);
+}
+
+int gprb_dataset_destroy(gprb_dataset* ds) {
+  if (!ds) return GPRB_OK;
+  cudaFree(ds->X); cudaFree(ds->Xt);
+  delete ds;
+  return GPRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int upload_targets(gprb_batch* b, const double* ymm) {
+  GPRB_CUDA(cudaMemsetAsync(b->ymm, 0, sizeof(double) * b->npad * b->B, b->stream[0]));
+  GPRB_CUDA(cudaMemcpy2DAsync(b->ymm, sizeof(double) * b->npad, ymm, sizeof(double) * b->n, sizeof(double) * b->n, b->B,
+                              cudaMemcpyHostToDevice, b->stream[0]));
+  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+  b->state_ok.assign(b->B, 0);
+  b->inv_ok.assign(b->B, 0);
+  return 0;
+}
+
+int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const double* ymm, int32_t kernel_kind,
+                      gprb_batch** out) {
+  GPRB_REQUIRE(ctx && ds && ymm && out, "gprb_batch_create: NULL argument");
+  *out = nullptr;
+  GPRB_REQUIRE(B >= 1 && B <= 65535, "gprb_batch_create: B must be in 1..65535");
+  GPRB_REQUIRE(kernel_kind >= 0 && kernel_kind <= 3, "gprb_batch_create: unknown kernel_kind");
+  for (int i = 0; i < B; ++i) {
+    GPRB_REQUIRE(ds[i] != nullptr, "gprb_batch_create: NULL dataset");
+    GPRB_REQUIRE(ds[i]->ctx == ctx, "gprb_batch_create: dataset belongs to another context");
+    GPRB_REQUIRE(ds[i]->n == ds[0]->n && ds[i]->d == ds[0]->d, "gprb_batch_create: datasets differ in n or d");
+  }
+  GPRB_CUDA(cudaSetDevice(ctx->device));
+  gprb_batch* b = new (std::nothrow) gprb_batch();
+  GPRB_REQUIRE(b != nullptr, "gprb_batch_create: out of host memory");
+  b->ctx = ctx; b->B = B; b->n = ds[0]->n; b->d = ds[0]->d; b->P = b->d + 2; b->kind = kernel_kind;
+  b->npad = ds[0]->npad; b->J = (int)(b->npad / NB);
+  b->ds.assign(ds, ds + B);
+  const size_t mat = (size_t)b->npad * b->npad, dinv = (size_t)b->J * NB * NB;
+  const size_t ntiles = (size_t)b->J * (b->J + 1) / 2;
+  int rc = 0;
+  do {
+    if ((rc = dev_alloc(&b->Xptr, B)) || (rc = dev_alloc(&b->Xtptr, B)) || (rc = dev_alloc(&b->ymm, (size_t)B * b->npad)) ||
+        (rc = dev_alloc(&b->theta, (size_t)B * b->P)) || (rc = dev_alloc(&b->A, mat * B)) || (rc = dev_alloc(&b->Lm, mat * B)) ||
+        (rc = dev_alloc(&b->Dinv, dinv * B)) || (rc = dev_alloc(&b->DinvT, dinv * B)) ||
+        (rc = dev_alloc(&b->alpha, (size_t)B * b->npad)) || (rc = dev_alloc(&b->zbuf, (size_t)B * b->npad)) ||
+        (rc = dev_alloc(&b->jitter, B)) || (rc = dev_alloc(&b->logdet_part, (size_t)B * b->J)) ||
+        (rc = dev_alloc(&b->fail, B)) || (rc = dev_alloc(&b->mll, B)) || (rc = dev_alloc(&b->grad, (size_t)B * b->P)) ||
+        (rc = dev_alloc(&b->grad_part, (size_t)B * ntiles * b->P)) || (rc = dev_alloc(&b->list, B)))
+      break;
+    b->stage_doubles = (int64_t)B * (b->P + 2);
+    cudaError_t e;
+    if ((e = cudaMallocHost((void**)&b->list_host, sizeof(int32_t) * B)) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&b->fail_host, sizeof(int32_t) * B)) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&b->stage_host, sizeof(double) * b->stage_doubles)) != cudaSuccess) {
+      rc = cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+      break;
+    }
+    b->nstreams = 4;
+    for (int s = 0; s < 4 && !rc; ++s) {
+      if ((e = cudaStreamCreateWithFlags(&b->stream[s], cudaStreamNonBlocking)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&b->join[s], cudaEventDisableTiming)) != cudaSuccess)
+        rc = cuda_fail(e, "stream/event create", __FILE__, __LINE__);
+    }
+    for (int s = 0; s < 8 && !rc; ++s)
+      if ((e = cudaEventCreate(&b->ev[s])) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
+    if (rc) break;
+    std::vector<const double*> xp(B), xtp(B);
+    for (int i = 0; i < B; ++i) { xp[i] = ds[i]->X; xtp[i] = ds[i]->Xt; }
+    if ((e = cudaMemcpy(b->Xptr, xp.data(), sizeof(double*) * B, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(b->Xtptr, xtp.data(), sizeof(double*) * B, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemset(b->theta, 0, sizeof(double) * B * b->P)) != cudaSuccess ||
+        (e = cudaMemset(b->jitter, 0, sizeof(double) * B)) != cudaSuccess ||
+        (e = cudaMemset(b->fail, 0, sizeof(int32_t) * B)) != cudaSuccess) {
+      rc = cuda_fail(e, "batch init copies", __FILE__, __LINE__);
+      break;
+    }
+    rc = upload_targets(b, ymm);
+  } while (0);
+  if (rc) { free_batch(b); return rc; }
+  *out = b;
+  return GPRB_OK;
+}
+
+int gprb_batch_set_targets(gprb_batch* b, const double* ymm) {
+  GPRB_REQUIRE(b && ymm, "gprb_batch_set_targets: NULL argument");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  return upload_targets(b, ymm);
+}
+
+int gprb_batch_destroy(gprb_batch* b) {
+  if (b) { cudaSetDevice(b->ctx->device); cudaDeviceSynchronize(); }
+  free_batch(b);
+  return GPRB_OK;
+}
+
+int gprb_set_profiling(gprb_batch* b, int32_t on) {
+  GPRB_REQUIRE(b, "gprb_set_profiling: NULL batch");
+  b->profiling = on != 0;
+  return GPRB_OK;
+}
+
+int gprb_last_stage_ms(gprb_batch* b, double out[6]) {
+  GPRB_REQUIRE(b && out, "gprb_last_stage_ms: NULL argument");
+  for (int i = 0; i < 6; ++i) out[i] = b->stage_ms[i];
+  return GPRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int gprb_eval(gprb_batch* b, const double* theta, const uint8_t* active, double* mll, double* grad, int32_t* info) {
+  GPRB_REQUIRE(b && theta && mll && info, "gprb_eval: NULL argument");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  const int B = b->B, P = b->P;
+  int count = 0;
+  for (int i = 0; i < B; ++i)
+    if (!active || active[i]) b->list_host[count++] = i;
+  // stage theta of the active GPs (pinned) and scatter with one strided copy per contiguous run
+  double* st = b->stage_host;
+  for (int k = 0; k < count; ++k) memcpy(st + (size_t)k * P, theta + (size_t)b->list_host[k] * P, sizeof(double) * P);
+  for (int k = 0; k < count;) {
+    int k2 = k + 1;
+    while (k2 < count && b->list_host[k2] == b->list_host[k2 - 1] + 1) ++k2;
+    GPRB_CUDA(cudaMemcpyAsync(b->theta + (size_t)b->list_host[k] * P, st + (size_t)k * P, sizeof(double) * P * (k2 - k),
+                              cudaMemcpyHostToDevice, b->stream[0]));
+    k = k2;
+  }
+  std::vector<int32_t> inf;
+  std::vector<int32_t> act(b->list_host, b->list_host + count);
+  int rc = evaluate_active(b, count, grad != nullptr, inf);
+  if (rc) return rc;
+  double* res = b->stage_host;  // [B] mll then [B*P] grad
+  GPRB_CUDA(cudaMemcpyAsync(res, b->mll, sizeof(double) * B, cudaMemcpyDeviceToHost, b->stream[0]));
+  if (grad) GPRB_CUDA(cudaMemcpyAsync(res + B, b->grad, sizeof(double) * B * P, cudaMemcpyDeviceToHost, b->stream[0]));
+  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+  const double ninf = -std::numeric_limits<double>::infinity(), qnan = std::numeric_limits<double>::quiet_NaN();
+  for (int gp : act) {
+    info[gp] = inf[gp];
+    const bool ok = inf[gp] >= 0;
+    mll[gp] = ok ? res[gp] : ninf;
+    if (grad)
+      for (int p = 0; p < P; ++p) grad[(size_t)gp * P + p] = ok ? res[B + (size_t)gp * P + p] : qnan;
+  }
+  return GPRB_OK;
+}
+
+int gprb_eval_device(gprb_batch* b, const double* theta_dev, double* mll_dev, double* grad_dev, int32_t* info_dev,
+                     void* stream) {
+  GPRB_REQUIRE(b && theta_dev && mll_dev, "gprb_eval_device: NULL argument");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  cudaStream_t user = (cudaStream_t)stream;
+  const int B = b->B, P = b->P;
+  // order after the caller's stream, run on the batch streams, hand results back on the caller's stream
+  GPRB_CUDA(cudaEventRecord(b->join[0], user));
+  GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[0], 0));
+  GPRB_CUDA(cudaMemcpyAsync(b->theta, theta_dev, sizeof(double) * B * P, cudaMemcpyDeviceToDevice, b->stream[0]));
+  for (int i = 0; i < B; ++i) b->list_host[i] = i;
+  std::vector<int32_t> inf;
+  int rc = evaluate_active(b, B, grad_dev != nullptr, inf);
+  if (rc) return rc;
+  GPRB_CUDA(cudaMemcpyAsync(mll_dev, b->mll, sizeof(double) * B, cudaMemcpyDeviceToDevice, b->stream[0]));
+  if (grad_dev) GPRB_CUDA(cudaMemcpyAsync(grad_dev, b->grad, sizeof(double) * B * P, cudaMemcpyDeviceToDevice, b->stream[0]));
+  if (info_dev) {
+    memcpy(b->fail_host, inf.data(), sizeof(int32_t) * B);
+    GPRB_CUDA(cudaMemcpyAsync(info_dev, b->fail_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, b->stream[0]));
+  }
+  GPRB_CUDA(cudaEventRecord(b->join[0], b->stream[0]));
+  GPRB_CUDA(cudaStreamWaitEvent(user, b->join[0], 0));
+  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+  return GPRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_stride, const double* mstar, double* mu,
+                 double* var) {
+  GPRB_REQUIRE(b && Xstar && mu, "gprb_predict: NULL argument");
+  GPRB_REQUIRE(m >= 1 && m <= (1 << 24), "gprb_predict: m out of range");
+  for (int i = 0; i < b->B; ++i)
+    GPRB_REQUIRE(b->state_ok[i], "gprb_predict: a GP has no evaluated state - call gprb_eval or gprb_optimize first");
+  GPRB_REQUIRE(xstar_stride == 0 || xstar_stride >= m * b->d, "gprb_predict: xstar_stride must be 0 or >= d*m");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  const int B = b->B;
+  cudaStream_t st = b->stream[0];
+  int ninv = 0;
+  if (var)
+    for (int i = 0; i < B; ++i)
+      if (!b->inv_ok[i]) b->list_host[ninv++] = i;
+  if (ninv > 0) {
+    // variance needs K^-1: run the inverse stage (TRTRI rows + LAUUM) on the resident factors that lack it
+    int rc = upload_list(b, ninv);
+    if (rc) return rc;
+    const int J = b->J;
+    GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->list, b->npad * b->npad, (int64_t)J * NB * NB,
+                (int)b->npad, J, 0, GEMM_TRTRI_ROW};
+    for (int i = 1; i < J; ++i) {
+      ga.step = i;
+      if ((rc = launch_tile_gemm(ga, i, ninv, st))) return rc;
+      b->ctx->launches++;
+    }
+    ga.mode = GEMM_LAUUM; ga.step = 0; ga.Cout = b->A;
+    if ((rc = launch_tile_gemm(ga, J * (J + 1) / 2, ninv, st))) return rc;
+    b->ctx->launches++;
+    for (int k = 0; k < ninv; ++k) b->inv_ok[b->list_host[k]] = 1;
+  }
+  const size_t nx = (size_t)(xstar_stride ? xstar_stride * (B - 1) + m * b->d : m * b->d);
+  double *dX = nullptr, *dms = nullptr, *dmu = nullptr, *dvar = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dev_alloc(&dX, nx)) || (rc = dev_alloc(&dmu, (size_t)B * m))) break;
+    if (mstar && (rc = dev_alloc(&dms, (size_t)B * m))) break;
+    if (var && (rc = dev_alloc(&dvar, (size_t)B * m))) break;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(dX, Xstar, sizeof(double) * nx, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D Xstar", __FILE__, __LINE__); break; }
+    if (mstar && (e = cudaMemcpyAsync(dms, mstar, sizeof(double) * B * m, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D mstar", __FILE__, __LINE__); break; }
+    PredictArgs pa{b->Xptr, b->theta, b->alpha, var ? b->A : nullptr, dX, dms, dmu, dvar, xstar_stride,
+                   b->npad * b->npad, (int)b->n, (int)b->npad, b->d, (int)m, b->kind};
+    if ((rc = launch_predict(pa, B, st))) break;
+    b->ctx->launches++;
+    if ((e = cudaMemcpyAsync(mu, dmu, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H mu", __FILE__, __LINE__); break; }
+    if (var && (e = cudaMemcpyAsync(var, dvar, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H var", __FILE__, __LINE__); break; }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "predict sync", __FILE__, __LINE__); break; }
+  } while (0);
+  cudaFree(dX); cudaFree(dms); cudaFree(dmu); cudaFree(dvar);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int fetch_matrix(gprb_batch* b, const double* dev, std::vector<double>& host) {
+  host.resize((size_t)b->npad * b->npad);
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+  GPRB_CUDA(cudaMemcpy(host.data(), dev, sizeof(double) * host.size(), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gprb_get_K(gprb_batch* b, int32_t gp, double* out) {
+  GPRB_REQUIRE(b && out && gp >= 0 && gp < b->B, "gprb_get_K: bad argument");
+  GPRB_REQUIRE(b->state_ok[gp], "gprb_get_K: no evaluated state");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  // K is overwritten by K^-1 after a gradient evaluation: re-assemble it (theta and jitter are resident)
+  double* scratch = nullptr;
+  int32_t* fl = nullptr;
+  int rc;
+  if ((rc = dev_alloc(&scratch, (size_t)b->npad * b->npad))) return rc;
+  if ((rc = dev_alloc(&fl, b->B))) { cudaFree(scratch); return rc; }
+  b->list_host[0] = gp;
+  rc = upload_list(b, 1);
+  if (!rc) {
+    // assemble GP `gp` into scratch: shift the base pointer so that gp * mat_stride lands on scratch
+    const int64_t ms = b->npad * b->npad;
+    AssembleArgs aa{b->Xtptr, b->theta, b->jitter, scratch - (int64_t)gp * ms, fl, b->list, ms, (int)b->n, (int)b->npad,
+                    b->d, b->J, b->kind};
+    rc = launch_assemble(aa, 1, b->stream[0]);
+  }
+  std::vector<double> h;
+  if (!rc) rc = fetch_matrix(b, scratch, h);
+  cudaFree(scratch); cudaFree(fl);
+  if (rc) return rc;
+  const int64_t n = b->n, np = b->npad;
+  for (int64_t c = 0; c < n; ++c)
+    for (int64_t r = c; r < n; ++r) out[r + c * n] = out[c + r * n] = h[r + c * np];
+  return GPRB_OK;
+}
+
+int gprb_get_chol(gprb_batch* b, int32_t gp, double* out) {
+  GPRB_REQUIRE(b && out && gp >= 0 && gp < b->B, "gprb_get_chol: bad argument");
+  GPRB_REQUIRE(b->state_ok[gp], "gprb_get_chol: no evaluated state");
+  std::vector<double> h;
+  int rc = fetch_matrix(b, b->Lm + (size_t)gp * b->npad * b->npad, h);
+  if (rc) return rc;
+  const int64_t n = b->n, np = b->npad;
+  for (int64_t c = 0; c < n; ++c)
+    for (int64_t r = 0; r < n; ++r) out[r + c * n] = (r <= c) ? h[c + r * np] : 0.0;  // U(r,c) = L(c,r)
+  return GPRB_OK;
+}
+
+int gprb_get_alpha(gprb_batch* b, int32_t gp, double* out) {
+  GPRB_REQUIRE(b && out && gp >= 0 && gp < b->B, "gprb_get_alpha: bad argument");
+  GPRB_REQUIRE(b->state_ok[gp], "gprb_get_alpha: no evaluated state");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+  GPRB_CUDA(cudaMemcpy(out, b->alpha + (size_t)gp * b->npad, sizeof(double) * b->n, cudaMemcpyDeviceToHost));
+  return GPRB_OK;
+}
+
+int gprb_get_Kinv(gprb_batch* b, int32_t gp, double* out) {
+  GPRB_REQUIRE(b && out && gp >= 0 && gp < b->B, "gprb_get_Kinv: bad argument");
+  GPRB_REQUIRE(b->inv_ok[gp], "gprb_get_Kinv: the last evaluation was value-only (no inverse resident)");
+  std::vector<double> h;
+  int rc = fetch_matrix(b, b->A + (size_t)gp * b->npad * b->npad, h);
+  if (rc) return rc;
+  const int64_t n = b->n, np = b->npad;
+  for (int64_t c = 0; c < n; ++c)
+    for (int64_t r = 0; r < n; ++r) out[r + c * n] = h[r + c * np];
+  return GPRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Shared definitions for libgprb200: handles, launch geometry, sm_100a PTX helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gprb200.h"
+
+namespace gprb {
+
+constexpr int NB = 128;        // tile edge of every blocked fp64 stage (Cholesky / TRTRI / LAUUM)
+constexpr int KT = 16;         // k-extent of one pipeline stage of the tile GEMM
+constexpr int LDS_T = NB + 4;  // padded smem row (doubles): (t*132 + g) mod 16 distinct over a half-warp
+constexpr int MAX_D = 64;      // 13 * bodies <= 52 in the reference (src/CState.jl:20); 64 leaves headroom
+constexpr int MAX_JITTER = 10; // make_posdef! retries (GaussianProcesses 0.12.4)
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define GPRB_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return ::gprb::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define GPRB_REQUIRE(cond, msg)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::gprb::set_error(msg);            \
+      return GPRB_ERR_ARG;               \
+    }                                    \
+  } while (0)
+
+}  // namespace gprb
+
+struct gprb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int clock_khz = 0;
+  int64_t l2_bytes = 0;
+  int64_t launches = 0;
+};
+
+struct gprb_dataset {
+  gprb_ctx* ctx = nullptr;
+  int64_t n = 0;
+  int32_t d = 0;
+  int64_t npad = 0;      // n rounded up to a multiple of NB
+  double* X = nullptr;   // device, d x n column-major (sample = contiguous column), tightly packed
+  double* Xt = nullptr;  // device, Xt[p][npad]: one contiguous, zero-padded row per input dimension (TMA source)
+};
+
+// Per-GP device state (structure-of-arrays over the batch), all resident in HBM:
+//   A   [B][npad*npad]  K (lower tiles) after assembly; K^-1 (lower tiles) after the inverse stage
+//   Lm  [B][npad*npad]  L (lower tiles, K = L L^T) and V = L^-T (strictly-upper tiles)
+//   Dinv/DinvT [B][J][NB*NB]  inverse of each diagonal block of L, and its transpose
+struct gprb_batch {
+  gprb_ctx* ctx = nullptr;
+  int32_t B = 0;
+  int64_t n = 0, npad = 0;
+  int32_t d = 0, J = 0, P = 0;
+  int32_t kind = 0;
+  std::vector<gprb_dataset*> ds;
+  const double** Xptr = nullptr;   // device array [B] of dataset X pointers
+  const double** Xtptr = nullptr;  // device array [B] of dataset Xt pointers
+  double* ymm = nullptr;          // [B][npad] (zero padded)
+  double* theta = nullptr;        // [B][P] theta of the last evaluation
+  double* A = nullptr;
+  double* Lm = nullptr;
+  double* Dinv = nullptr;
+  double* DinvT = nullptr;
+  double* alpha = nullptr;        // [B][npad]
+  double* zbuf = nullptr;         // [B][npad] forward-substitution result
+  double* jitter = nullptr;       // [B] cumulative diagonal jitter added this evaluation
+  double* logdet_part = nullptr;  // [B][J]
+  int32_t* fail = nullptr;        // [B] 0 ok / first failing column+1 (LAPACK info)
+  int32_t* info = nullptr;        // [B] device copy of the per-GP info
+  double* mll = nullptr;          // [B]
+  double* grad = nullptr;         // [B][P]
+  double* grad_part = nullptr;    // [B][ntiles][P+1] per-tile partial sums (deterministic 2-pass reduction)
+  int32_t* list = nullptr;        // [B] compact list of GP indices a launch works on
+  int32_t* list_host = nullptr;   // pinned
+  int32_t* fail_host = nullptr;   // pinned
+  double* stage_host = nullptr;   // pinned staging for theta / results
+  int64_t stage_doubles = 0;
+  cudaStream_t stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nstreams = 1;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t join[4] = {};
+  bool profiling = false;
+  std::vector<uint8_t> state_ok;  // per GP: factor + alpha resident (last evaluation succeeded)
+  std::vector<uint8_t> inv_ok;    // per GP: K^-1 resident in A (last evaluation was value+gradient)
+  double stage_ms[6] = {0, 0, 0, 0, 0, 0};
+};
+
+// --------------------------------------------------------------------------------------
+// device-side PTX helpers (sm_100a): mbarrier, bulk async copy (TMA engine, SASS UBLKCP), DMMA
+// --------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace gprb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion counted in bytes on `bar`.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Order generic-proxy smem writes before later async-proxy (TMA) accesses to the same smem.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col) in fp64 on the tensor pipe (SASS DMMA.8x8x4).
+// lane = 4*g + t : a = A[g][t], b = B[t][g] (i.e. "B^T row g, col t"), c0/c1 = D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+}  // namespace gprb
+#endif

@@ -1,0 +1,335 @@
+// K1 covariance assembly and K5 fused log-marginal-likelihood gradient.
+//
+// Both are pairwise kernels over 128x128 tiles of sample pairs.  The two d x 128 input tiles are staged
+// by the TMA engine (one 1 KB bulk copy per input dimension from the dataset's transposed copy Xt[d][npad],
+// completion on an mbarrier); each thread then owns an 8x8 block of pairs in registers.
+// Distances follow the reference's direct-difference form  r2 = sum_p w_p (x_ip - x_jp)^2  (never the
+// |x|^2 + |x'|^2 - 2 x.x' expansion, which loses 1e-12 parity on near-duplicate trajectory samples).
+// The gradient kernel never materialises Q = alpha alpha' - K^-1 or dK/dtheta:
+//     g_noise = s_n^2 tr(Q),  g_ll_p = 1/2 w_p sum_ij Q_ij g(r_ij) (x_ip - x_jp)^2,  g_lsigma = sum_ij Q_ij K_f,ij
+// Per-tile partial sums are written to HBM and reduced in a fixed order by a second kernel (deterministic).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gprb {
+
+constexpr int PW_THREADS = 256;
+constexpr double EPS_F64 = 2.220446049250313e-16;
+
+template <int KIND>
+__device__ __forceinline__ void kfun(double r2, double sf2, double& kf, double& gf) {
+  if (KIND == GPRB_KERNEL_SE_ARD) {
+    kf = sf2 * exp(-0.5 * r2);
+    gf = kf;
+  } else if (KIND == GPRB_KERNEL_MAT12_ARD) {
+    const double r = sqrt(r2);
+    kf = sf2 * exp(-r);
+    gf = r > 0.0 ? kf / r : 0.0;
+  } else if (KIND == GPRB_KERNEL_MAT32_ARD) {
+    const double s = 1.7320508075688772 * sqrt(r2);
+    const double e = exp(-s);
+    kf = sf2 * (1.0 + s) * e;
+    gf = 3.0 * sf2 * e;
+  } else {
+    const double s = 2.23606797749979 * sqrt(r2);
+    const double e = exp(-s);
+    kf = sf2 * (1.0 + s + 5.0 * r2 / 3.0) * e;
+    gf = (5.0 / 3.0) * sf2 * (1.0 + s) * e;
+  }
+}
+
+__device__ __forceinline__ void lower_tile(int bx, int& i, int& j) {
+  i = (int)((sqrt(8.0 * bx + 1.0) - 1.0) * 0.5);
+  while ((i + 1) * (i + 2) / 2 <= bx) ++i;
+  while (i * (i + 1) / 2 > bx) --i;
+  j = bx - i * (i + 1) / 2;
+}
+
+// Stage Xt[:, i*128 .. +128] and Xt[:, j*128 .. +128] into smem as Xi[p][128], Xj[p][128].
+__device__ __forceinline__ void stage_inputs(const double* Xt, int npad, int d, int i, int j, double* Xi, double* Xj,
+                                             uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(2 * d * NB * sizeof(double)));
+  __syncthreads();
+  for (int p = threadIdx.x; p < 2 * d; p += blockDim.x) {
+    const int q = p < d ? p : p - d;
+    const int blk = p < d ? i : j;
+    bulk_g2s((p < d ? Xi : Xj) + q * NB, Xt + (int64_t)q * npad + (int64_t)blk * NB, NB * sizeof(double), bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// r2[a][b] for the thread's 8x8 pair block: rows {2tx,2tx+1}+32*ra, cols {2ty,2ty+1}+32*cb.
+__device__ __forceinline__ void pair_r2(const double* Xi, const double* Xj, const double* w, int d, int tx, int ty,
+                                        double (&r2)[8][8]) {
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) r2[a][b] = 0.0;
+  for (int p = 0; p < d; ++p) {
+    double xr[8], xc[8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
+      xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
+      const double2 u = *reinterpret_cast<const double2*>(Xj + p * NB + 32 * a + 2 * ty);
+      xc[2 * a] = u.x; xc[2 * a + 1] = u.y;
+    }
+    const double wp = w[p];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const double df = xr[a] - xc[b];
+        r2[a][b] = fma(wp, df * df, r2[a][b]);
+      }
+  }
+}
+
+__device__ __forceinline__ int loc8(int a, int t) { return 32 * (a >> 1) + 2 * t + (a & 1); }
+
+template <int KIND>
+__global__ void __launch_bounds__(PW_THREADS, 1) k_assemble(AssembleArgs g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Xi = reinterpret_cast<double*>(smem_raw);
+  double* Xj = Xi + g.d * NB;
+  double* w = Xj + g.d * NB;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(w + MAX_D);
+  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  int ti, tj;
+  lower_tile(blockIdx.x, ti, tj);
+  const double* th = g.theta + (int64_t)gp * (g.d + 2);
+  if (threadIdx.x < g.d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
+  stage_inputs(g.Xt[gp], g.npad, g.d, ti, tj, Xi, Xj, bar);
+  __syncthreads();
+  const double sf2 = exp(2.0 * th[g.d + 1]);
+  const double diag_add = exp(2.0 * th[0]) + EPS_F64 + g.jitter[gp];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // info -2: non-finite theta / kernel scale (also resets the flag)
+    bool ok = isfinite(sf2) && isfinite(diag_add);
+    for (int p = 0; p < g.d + 2; ++p) ok = ok && isfinite(th[p]);
+    for (int p = 0; p < g.d; ++p) ok = ok && isfinite(w[p]);
+    g.fail[gp] = ok ? 0 : -2;
+  }
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double r2[8][8];
+  pair_r2(Xi, Xj, w, g.d, tx, ty, r2);
+  double* A = g.A + (int64_t)gp * g.mat_stride;
+  const int n = g.n;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int c = tj * NB + loc8(b, ty);
+#pragma unroll
+    for (int a = 0; a < 8; a += 2) {
+      const int r = ti * NB + loc8(a, tx);
+      double v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double kf, gf;
+        kfun<KIND>(r2[a + e][b], sf2, kf, gf);
+        const int rr = r + e;
+        if (rr == c) kf += diag_add;
+        if (rr >= n || c >= n) kf = (rr == c) ? 1.0 : 0.0;
+        v[e] = kf;
+      }
+      *reinterpret_cast<double2*>(A + r + (int64_t)c * g.npad) = make_double2(v[0], v[1]);
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PW_THREADS, 1) k_grad_tiles(GradArgs g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = g.d;
+  double* Xi = reinterpret_cast<double*>(smem_raw);
+  double* Xj = Xi + d * NB;
+  double* w = Xj + d * NB;
+  double* red = w + MAX_D;                 // [(d + 2)][PW_THREADS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + (d + 2) * PW_THREADS);
+  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  int ti, tj;
+  lower_tile(blockIdx.x, ti, tj);
+  const double* th = g.theta + (int64_t)gp * (d + 2);
+  if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
+  stage_inputs(g.Xt[gp], g.npad, d, ti, tj, Xi, Xj, bar);
+  __syncthreads();
+  const double sf2 = exp(2.0 * th[d + 1]);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double m[8][8];
+  pair_r2(Xi, Xj, w, d, tx, ty, m);  // m holds r2 for now
+  const double* Kinv = g.Kinv + (int64_t)gp * g.mat_stride;
+  const double* alpha = g.alpha + (int64_t)gp * g.npad;
+  const int n = g.n;
+  double s_sig = 0.0, s_tr = 0.0;
+  double ar[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) ar[a] = alpha[ti * NB + loc8(a, tx)];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int c = tj * NB + loc8(b, ty);
+    const double ac = alpha[c];
+#pragma unroll
+    for (int a = 0; a < 8; a += 2) {
+      const int r = ti * NB + loc8(a, tx);
+      const double2 kv = *reinterpret_cast<const double2*>(Kinv + r + (int64_t)c * g.npad);
+      const double kin[2] = {kv.x, kv.y};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double kf, gf;
+        kfun<KIND>(m[a + e][b], sf2, kf, gf);
+        const int rr = r + e;
+        double q = ar[a + e] * ac - kin[e];
+        if (rr >= n || c >= n) q = 0.0;
+        s_sig = fma(q, kf, s_sig);
+        if (rr == c) s_tr += q;
+        m[a + e][b] = q * gf;
+      }
+    }
+  }
+  // pass 2: per-dimension weighted sums; one scalar per (p, thread) parked in smem
+  for (int p = 0; p < d; ++p) {
+    double xr[8], xc[8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
+      xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
+      const double2 u = *reinterpret_cast<const double2*>(Xj + p * NB + 32 * a + 2 * ty);
+      xc[2 * a] = u.x; xc[2 * a + 1] = u.y;
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a += 2)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const double d0 = xr[a] - xc[b], d1 = xr[a + 1] - xc[b];
+        s0 = fma(m[a][b], d0 * d0, s0);
+        s1 = fma(m[a + 1][b], d1 * d1, s1);
+      }
+    red[p * PW_THREADS + threadIdx.x] = s0 + s1;
+  }
+  red[d * PW_THREADS + threadIdx.x] = s_sig;
+  red[(d + 1) * PW_THREADS + threadIdx.x] = s_tr;
+  __syncthreads();
+  // fixed-order block reduction: warp v sums rows v, v+8, ...
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double wt = (ti == tj) ? 1.0 : 2.0;
+  const int ntiles = g.J * (g.J + 1) / 2;
+  double* part = g.part + ((int64_t)gp * ntiles + blockIdx.x) * (d + 2);
+  for (int row = warp; row < d + 2; row += PW_THREADS / 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < PW_THREADS / 32; ++k) s += red[row * PW_THREADS + lane + 32 * k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+      // part layout: [0] trace(Q) part, [1..d] sum Q g Delta_p^2, [d+1] sum Q K_f
+      if (row < d) part[1 + row] = wt * s;
+      else if (row == d) part[d + 1] = wt * s;
+      else part[0] = s;  // trace lives on diagonal tiles only (weight 1)
+    }
+  }
+}
+
+__global__ void k_grad_reduce(GradArgs g) {
+  const int gp = g.list ? g.list[blockIdx.x] : blockIdx.x;
+  const int d = g.d, P = d + 2;
+  const int ntiles = g.J * (g.J + 1) / 2;
+  const double* th = g.theta + (int64_t)gp * P;
+  const double* part = g.part + (int64_t)gp * ntiles * P;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    double s = 0.0;
+    for (int t = 0; t < ntiles; ++t) s += part[(int64_t)t * P + p];
+    double v;
+    if (p == 0) v = exp(2.0 * th[0]) * s;                 // dmll_noise: exp(2 logNoise) tr(Q), no eps
+    else if (p <= d) v = 0.5 * exp(-2.0 * th[p]) * s;      // 1/2 w_p sum Q g Delta_p^2
+    else v = s;                                            // dK/dlsigma = 2 K_f
+    if (g.fail[gp] != 0) v = __longlong_as_double(0x7ff8000000000000LL);
+    g.grad[(int64_t)gp * P + p] = v;
+  }
+}
+
+__global__ void k_transpose_inputs(const double* X, double* Xt, int n, int npad, int d) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)npad * d) return;
+  const int p = (int)(idx / npad), r = (int)(idx % npad);
+  Xt[idx] = r < n ? X[(int64_t)r * d + p] : 0.0;
+}
+
+// make_posdef!: K_ii += 1e-6 tr(K)/n, cumulative.  For a stationary kernel tr(K)/n = s_f^2 + (s_n^2 + eps + jitter)
+// exactly, so the increment needs no pass over the matrix; the next assembly applies it.
+__global__ void k_add_jitter(const double* theta, double* jitter, const int32_t* list, int d, int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int gp = list[k];
+  const double* th = theta + (int64_t)gp * (d + 2);
+  const double mean_diag = exp(2.0 * th[d + 1]) + exp(2.0 * th[0]) + EPS_F64 + jitter[gp];
+  jitter[gp] += 1e-6 * mean_diag;
+}
+
+static size_t pw_smem(int d, bool grad) {
+  size_t doubles = (size_t)2 * d * NB + MAX_D + (grad ? (size_t)(d + 2) * PW_THREADS : 0);
+  return doubles * sizeof(double) + 16;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", __FILE__, __LINE__);
+  return 0;
+}
+
+int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  const size_t smem = pw_smem(a.d, false);
+  dim3 grid(a.J * (a.J + 1) / 2, count);
+  int rc = 0;
+  switch (a.kind) {
+    case GPRB_KERNEL_SE_ARD: rc = set_smem(k_assemble<0>, smem); if (!rc) k_assemble<0><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    case GPRB_KERNEL_MAT12_ARD: rc = set_smem(k_assemble<1>, smem); if (!rc) k_assemble<1><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    case GPRB_KERNEL_MAT32_ARD: rc = set_smem(k_assemble<2>, smem); if (!rc) k_assemble<2><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    default: rc = set_smem(k_assemble<3>, smem); if (!rc) k_assemble<3><<<grid, PW_THREADS, smem, stream>>>(a); break;
+  }
+  if (rc) return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_assemble launch", __FILE__, __LINE__);
+  return 0;
+}
+
+int launch_grad(const GradArgs& a, int count, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  const size_t smem = pw_smem(a.d, true);
+  dim3 grid(a.J * (a.J + 1) / 2, count);
+  int rc = 0;
+  switch (a.kind) {
+    case GPRB_KERNEL_SE_ARD: rc = set_smem(k_grad_tiles<0>, smem); if (!rc) k_grad_tiles<0><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    case GPRB_KERNEL_MAT12_ARD: rc = set_smem(k_grad_tiles<1>, smem); if (!rc) k_grad_tiles<1><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    case GPRB_KERNEL_MAT32_ARD: rc = set_smem(k_grad_tiles<2>, smem); if (!rc) k_grad_tiles<2><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    default: rc = set_smem(k_grad_tiles<3>, smem); if (!rc) k_grad_tiles<3><<<grid, PW_THREADS, smem, stream>>>(a); break;
+  }
+  if (rc) return rc;
+  k_grad_reduce<<<count, 64, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_grad launch", __FILE__, __LINE__);
+  return 0;
+}
+
+int launch_transpose_inputs(const double* X, double* Xt, int n, int npad, int d, cudaStream_t stream) {
+  const int64_t total = (int64_t)npad * d;
+  k_transpose_inputs<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(X, Xt, n, npad, d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_transpose_inputs launch", __FILE__, __LINE__);
+  return 0;
+}
+
+int launch_add_jitter(const double* theta, double* jitter, const int32_t* list, int d, int count, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  k_add_jitter<<<(count + 127) / 128, 128, 0, stream>>>(theta, jitter, list, d, count);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_add_jitter launch", __FILE__, __LINE__);
+  return 0;
+}
+
+}  // namespace gprb

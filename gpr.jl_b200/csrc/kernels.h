@@ -1,0 +1,100 @@
+// Launcher prototypes of the libgprb200 CUDA stages (host-callable, defined in the .cu files).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gprb {
+
+enum { GEMM_CHOL_DIAG = 0, GEMM_CHOL_COL = 1, GEMM_TRTRI_ROW = 2, GEMM_LAUUM = 3 };
+
+struct GemmArgs {
+  const double* Lm;     // operand matrices [B][npad*npad]
+  const double* DinvT;  // transposed inverse diagonal blocks [B][J][NB*NB] (operand substitute for V(k,k))
+  const double* Dinv;   // inverse diagonal blocks (post-multiplier)
+  const double* Cin;    // K tiles for the Cholesky modes
+  double* Cout;
+  const int32_t* list;  // GP index per blockIdx.y (nullptr = identity)
+  int64_t mat_stride, dinv_stride;
+  int npad, J, step, mode;
+};
+
+int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream);
+
+// K1: covariance assembly, lower tiles of K = K_f + (exp(2 logNoise) + eps + jitter) I ; identity in the padding.
+struct AssembleArgs {
+  const double* const* Xt;  // [B] per-GP pointer to the dataset's transposed inputs Xt[d][npad]
+  const double* theta;      // [B][P]
+  const double* jitter;     // [B]
+  double* A;                // [B][npad*npad]
+  int32_t* fail;            // [B] reset here: 0, or -2 for non-finite theta
+  const int32_t* list;
+  int64_t mat_stride;
+  int n, npad, d, J, kind;
+};
+int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream);
+
+// potf2 + trtri of the 128x128 diagonal block `step` (in place in Lm), emits Dinv, DinvT, logdet partials, fail flag.
+struct DiagArgs {
+  double* Lm;
+  double* Dinv;
+  double* DinvT;
+  double* logdet_part;  // [B][J]
+  int32_t* fail;        // [B]
+  const int32_t* list;
+  int64_t mat_stride, dinv_stride;
+  int npad, J, step;
+};
+int launch_diag_factor(const DiagArgs& a, int count, cudaStream_t stream);
+
+// forward + backward substitution, alpha = K^-1 ymm, and mll = -1/2 (ymm'alpha + logdet + n log 2pi).
+struct SolveArgs {
+  const double* Lm;
+  const double* Dinv;
+  const double* ymm;          // [B][npad]
+  const double* logdet_part;  // [B][J]
+  const int32_t* fail;
+  double* zbuf;               // [B][npad]
+  double* alpha;              // [B][npad]
+  double* mll;                // [B]
+  const int32_t* list;
+  int64_t mat_stride, dinv_stride;
+  int n, npad, J;
+};
+int launch_solve(const SolveArgs& a, int count, cudaStream_t stream);
+
+// K5: fused gradient  d mll / d theta = 1/2 tr((alpha alpha' - K^-1) dK/dtheta), never materialising dK.
+struct GradArgs {
+  const double* const* Xt;
+  const double* theta;
+  const double* Kinv;   // A buffer, full symmetric K^-1
+  const double* alpha;
+  double* part;         // [B][ntiles][P + 1]
+  double* grad;         // [B][P]
+  const int32_t* fail;
+  const int32_t* list;
+  int64_t mat_stride;
+  int n, npad, d, J, kind;
+};
+int launch_grad(const GradArgs& a, int count, cudaStream_t stream);
+
+// dataset helpers
+int launch_transpose_inputs(const double* X, double* Xt, int n, int npad, int d, cudaStream_t stream);
+// jitter[gp] += 1e-6 * tr(K)/n for the listed GPs (make_posdef!); applied by the next assembly
+int launch_add_jitter(const double* theta, double* jitter, const int32_t* list, int d, int count, cudaStream_t stream);
+
+// K6: posterior mean / variance
+struct PredictArgs {
+  const double* const* X;  // [B] original d x n inputs
+  const double* theta;
+  const double* alpha;
+  const double* Kinv;      // nullptr => mean only
+  const double* Xstar;     // d x m (+ b * xstar_stride)
+  const double* mstar;     // [B][m] or nullptr
+  double* mu;              // [B][m]
+  double* var;             // [B][m] or nullptr
+  int64_t xstar_stride, mat_stride;
+  int n, npad, d, m, kind;
+};
+int launch_predict(const PredictArgs& a, int B, cudaStream_t stream);
+
+}  // namespace gprb

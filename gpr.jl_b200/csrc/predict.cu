@@ -1,0 +1,155 @@
+// K6 posterior prediction (reference call examples/utils/predictdynamics.jl:13):
+//   k*_r = k(X[:,r], x*) ;  mu* = m(x*) + k*' alpha ;  var* = max(s_f^2 - k*' K^-1 k*, 0) + exp(2 logNoise)
+// One CTA handles PS test columns of one GP: cross-covariances are built once into shared memory, the mean is
+// a fused dot product, and the variance streams K^-1 once per CTA (8 test columns share every matrix element).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gprb {
+
+constexpr int PS = 8;  // test columns per CTA
+constexpr int PRED_THREADS = 256;
+
+template <int KIND>
+__device__ __forceinline__ double kcross(double r2, double sf2) {
+  if (KIND == GPRB_KERNEL_SE_ARD) return sf2 * exp(-0.5 * r2);
+  const double r = sqrt(r2);
+  if (KIND == GPRB_KERNEL_MAT12_ARD) return sf2 * exp(-r);
+  if (KIND == GPRB_KERNEL_MAT32_ARD) { const double s = 1.7320508075688772 * r; return sf2 * (1.0 + s) * exp(-s); }
+  const double s = 2.23606797749979 * r;
+  return sf2 * (1.0 + s + 5.0 * r2 / 3.0) * exp(-s);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int k = 0; k < PRED_THREADS / 32; ++k) s += red[k];
+  return s;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* ks = reinterpret_cast<double*>(smem_raw);  // [PS][npad]
+  double* xs = ks + (size_t)PS * g.npad;              // [PS][d]
+  double* w = xs + PS * MAX_D;                        // [d]
+  double* red = w + MAX_D;                            // [8]
+  const int gp = blockIdx.y;
+  const int s0 = blockIdx.x * PS;
+  const int ns = min(PS, g.m - s0);
+  const int d = g.d, n = g.n, npad = g.npad;
+  const double* th = g.theta + (int64_t)gp * (d + 2);
+  const double* Xstar = g.Xstar + (int64_t)gp * g.xstar_stride;
+  for (int idx = threadIdx.x; idx < PS * d; idx += PRED_THREADS) {
+    const int s = idx / d, p = idx % d;
+    xs[s * MAX_D + p] = s < ns ? Xstar[(int64_t)(s0 + s) * d + p] : 0.0;
+  }
+  if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
+  __syncthreads();
+  const double sf2 = exp(2.0 * th[d + 1]);
+  const double* X = g.X[gp];
+  const double* alpha = g.alpha + (int64_t)gp * npad;
+  double mu_acc[PS];
+#pragma unroll
+  for (int s = 0; s < PS; ++s) mu_acc[s] = 0.0;
+  for (int r = threadIdx.x; r < npad; r += PRED_THREADS) {
+    double r2[PS];
+#pragma unroll
+    for (int s = 0; s < PS; ++s) r2[s] = 0.0;
+    if (r < n) {
+      const double* xr = X + (int64_t)r * d;
+      for (int p = 0; p < d; ++p) {
+        const double xv = xr[p], wp = w[p];
+#pragma unroll
+        for (int s = 0; s < PS; ++s) {
+          const double df = xv - xs[s * MAX_D + p];
+          r2[s] = fma(wp, df * df, r2[s]);
+        }
+      }
+    }
+    const double ar = alpha[r];
+#pragma unroll
+    for (int s = 0; s < PS; ++s) {
+      const double kv = (r < n) ? kcross<KIND>(r2[s], sf2) : 0.0;
+      ks[(size_t)s * npad + r] = kv;
+      mu_acc[s] = fma(kv, ar, mu_acc[s]);
+    }
+  }
+  for (int s = 0; s < PS; ++s) {
+    const double tot = block_sum(mu_acc[s], red);
+    if (threadIdx.x == 0 && s < ns) {
+      const int64_t o = (int64_t)gp * g.m + s0 + s;
+      g.mu[o] = tot + (g.mstar ? g.mstar[o] : 0.0);
+    }
+  }
+  if (g.var == nullptr) return;
+  __syncthreads();
+  // quadratic form q_s = sum_r k_r (sum_c Kinv[r][c] k_c): thread owns rows, streams columns (coalesced over rows)
+  const double* Kinv = g.Kinv + (int64_t)gp * g.mat_stride;
+  double q[PS];
+#pragma unroll
+  for (int s = 0; s < PS; ++s) q[s] = 0.0;
+  for (int r = threadIdx.x; r < n; r += PRED_THREADS) {
+    double t[PS];
+#pragma unroll
+    for (int s = 0; s < PS; ++s) t[s] = 0.0;
+    const double* Kr = Kinv + r;
+    int c = 0;
+    for (; c + 3 < n; c += 4) {
+      const double k0 = Kr[(int64_t)c * npad], k1 = Kr[(int64_t)(c + 1) * npad];
+      const double k2 = Kr[(int64_t)(c + 2) * npad], k3 = Kr[(int64_t)(c + 3) * npad];
+#pragma unroll
+      for (int s = 0; s < PS; ++s) {
+        const double* kc = ks + (size_t)s * npad + c;
+        t[s] = fma(k0, kc[0], t[s]);
+        t[s] = fma(k1, kc[1], t[s]);
+        t[s] = fma(k2, kc[2], t[s]);
+        t[s] = fma(k3, kc[3], t[s]);
+      }
+    }
+    for (; c < n; ++c) {
+      const double k0 = Kr[(int64_t)c * npad];
+#pragma unroll
+      for (int s = 0; s < PS; ++s) t[s] = fma(k0, ks[(size_t)s * npad + c], t[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < PS; ++s) q[s] = fma(ks[(size_t)s * npad + r], t[s], q[s]);
+  }
+  const double sn2 = exp(2.0 * th[0]);
+  for (int s = 0; s < PS; ++s) {
+    const double tot = block_sum(q[s], red);
+    if (threadIdx.x == 0 && s < ns) g.var[(int64_t)gp * g.m + s0 + s] = fmax(sf2 - tot, 0.0) + sn2;
+  }
+}
+
+int launch_predict(const PredictArgs& a, int B, cudaStream_t stream) {
+  if (B <= 0 || a.m <= 0) return 0;
+  const size_t smem = ((size_t)PS * a.npad + PS * MAX_D + MAX_D + 8) * sizeof(double);
+  if (smem > 227 * 1024) {
+    set_error("gprb_predict: n too large for the shared-memory cross-covariance block (npad <= 3500)");
+    return GPRB_ERR_ARG;
+  }
+  dim3 grid((a.m + PS - 1) / PS, B);
+  cudaError_t e;
+#define GPRB_PRED_CASE(K)                                                                                   \
+  e = cudaFuncSetAttribute(k_predict<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_predict)", __FILE__, __LINE__);         \
+  k_predict<K><<<grid, PRED_THREADS, smem, stream>>>(a);
+  switch (a.kind) {
+    case GPRB_KERNEL_SE_ARD: GPRB_PRED_CASE(0) break;
+    case GPRB_KERNEL_MAT12_ARD: GPRB_PRED_CASE(1) break;
+    case GPRB_KERNEL_MAT32_ARD: GPRB_PRED_CASE(2) break;
+    default: GPRB_PRED_CASE(3) break;
+  }
+#undef GPRB_PRED_CASE
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_predict launch", __FILE__, __LINE__);
+  return 0;
+}
+
+}  // namespace gprb

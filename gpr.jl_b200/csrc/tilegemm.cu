@@ -1,0 +1,284 @@
+// Batched fp64 tile GEMM (NT form) on the DMMA tensor pipe - the engine of the blocked
+// Cholesky (row a6), the triangular inverse and the LAUUM product (row a8) of SURVEY.md section 8a.
+//
+// One CTA = one 128x128 output tile of one GP:
+//     acc = sum_{k-blocks} Aop[i-rows, k] * Bop[j-rows, k]^T          (both operands column-major, ld = npad)
+// Warp-specialised: warp 8 is the producer (1 KB bulk copies through the TMA engine, one operand
+// column each, completion counted on mbarriers), warps 0-7 are DMMA consumers with 64x32 register
+// tiles (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, the native fp64 tensor shape on sm_100a).
+// Padded smem rows (132 doubles) make every fragment load bank-conflict free.
+//
+// Modes (tile coordinates and k-range derive from `mode`, `step` and blockIdx.x):
+//   CHOL_DIAG  S(j,j)   = K(j,j) - sum_{k<j} L(j,k) L(j,k)^T                      -> Lm(j,j)   (potf2 follows)
+//   CHOL_COL   L(i,j)   = [K(i,j) - sum_{k<j} L(i,k) L(j,k)^T] * inv(L_jj)^T      -> Lm(i,j)   i > j = step
+//   TRTRI_ROW  W(i,j)   = -inv(L_ii) * sum_{k=j}^{i-1} L(i,k) W(k,j)   stored as V(j,i) = W(i,j)^T, i = step
+//   LAUUM      Kinv(i,j) = sum_{k>=i} V(i,k) V(j,k)^T  (i >= j), mirrored to (j,i) -> A
+// where V = L^-T lives in the strictly-upper tiles of Lm and its diagonal blocks in DinvT.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gprb {
+
+constexpr int NSTAGE = 4;
+constexpr int STAGE_DOUBLES = 2 * KT * LDS_T;           // A + B operand chunk
+constexpr int RBUF_DOUBLES = KT * LDS_T;                // one chunk of the post-multiplier
+constexpr int N_CONSUMER_WARPS = 8;
+constexpr int GEMM_THREADS = (N_CONSUMER_WARPS + 1) * 32;
+static_assert(NSTAGE * STAGE_DOUBLES == NB * LDS_T, "T tile must exactly reuse the stage ring");
+constexpr size_t GEMM_SMEM = (size_t)(NSTAGE * STAGE_DOUBLES + 2 * RBUF_DOUBLES) * sizeof(double) + 16 * sizeof(uint64_t);
+
+struct TileCoord {
+  int i, j;        // output tile (block row, block col)
+  int kb0, kb1;    // k-block range [kb0, kb1)
+  int a_diag_kb;   // k-block whose A operand comes from DinvT (-1: none)
+  int b_diag_kb;   // same for B
+  int post;        // 0 none, 1 right-multiply by Dinv[rblk]^T, 2 left-multiply by -Dinv[rblk]
+  int rblk;
+  bool use_cin;    // T = Cin - acc, else T = acc
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int bx) {
+  TileCoord tc;
+  tc.a_diag_kb = tc.b_diag_kb = -1;
+  tc.post = 0;
+  tc.rblk = 0;
+  tc.use_cin = false;
+  if (mode == GEMM_CHOL_DIAG) {
+    tc.i = tc.j = step; tc.kb0 = 0; tc.kb1 = step; tc.use_cin = true;
+  } else if (mode == GEMM_CHOL_COL) {
+    tc.i = step + 1 + bx; tc.j = step; tc.kb0 = 0; tc.kb1 = step; tc.use_cin = true; tc.post = 1; tc.rblk = step;
+  } else if (mode == GEMM_TRTRI_ROW) {
+    tc.i = step; tc.j = bx; tc.kb0 = bx; tc.kb1 = step; tc.b_diag_kb = bx; tc.post = 2; tc.rblk = step;
+  } else {  // GEMM_LAUUM: bx enumerates (i, j), j <= i, row by row => longest k-range first
+    int i = (int)((sqrt(8.0 * bx + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= bx) ++i;
+    while (i * (i + 1) / 2 > bx) --i;
+    tc.i = i; tc.j = bx - i * (i + 1) / 2; tc.kb0 = i; tc.kb1 = J; tc.a_diag_kb = i;
+    tc.b_diag_kb = (tc.j == i) ? i : -1;
+  }
+  return tc;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* rbuf = stages + NSTAGE * STAGE_DOUBLES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + 2 * RBUF_DOUBLES);
+  uint64_t* full = bars;            // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;  // [NSTAGE]
+  uint64_t* rfull = bars + 2 * NSTAGE;      // [2]
+  uint64_t* rempty = bars + 2 * NSTAGE + 2; // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  const TileCoord tc = tile_coord(g.mode, g.step, g.J, blockIdx.x);
+  const int64_t npad = g.npad;
+  const double* Lm = g.Lm + (int64_t)gp * g.mat_stride;
+  const double* DinvT = g.DinvT + (int64_t)gp * g.dinv_stride;
+  const double* Dinv = g.Dinv + (int64_t)gp * g.dinv_stride;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], N_CONSUMER_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], N_CONSUMER_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int nchunks = (tc.kb1 - tc.kb0) * (NB / KT);
+
+  if (warp == N_CONSUMER_WARPS) {
+    // ===================== producer warp =====================
+    int stage = 0; uint32_t phase = 0;
+    int rissued = 0;
+    auto issue_r = [&](int c) {  // chunk c of the post-multiplier -> rbuf[c & 1]
+      const int buf = c & 1;
+      mbar_wait(&rempty[buf], ((c >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&rfull[buf], KT * NB * sizeof(double));
+      __syncwarp();
+      if (lane < KT) {
+        const double* src = Dinv + (int64_t)tc.rblk * NB * NB + (int64_t)(c * KT + lane) * NB;
+        bulk_g2s(rbuf + buf * RBUF_DOUBLES + lane * LDS_T, src, NB * sizeof(double), &rfull[buf]);
+      }
+    };
+    if (tc.post) { issue_r(0); issue_r(1); rissued = 2; }
+    for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+      const double* srcA; const double* srcB; int64_t ldA, ldB;
+      if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }
+      else { srcA = Lm + (int64_t)tc.i * NB + (int64_t)kb * NB * npad; ldA = npad; }
+      if (kb == tc.b_diag_kb) { srcB = DinvT + (int64_t)kb * NB * NB; ldB = NB; }
+      else { srcB = Lm + (int64_t)tc.j * NB + (int64_t)kb * NB * npad; ldB = npad; }
+      for (int c = 0; c < NB / KT; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) mbar_expect_tx(&full[stage], 2 * KT * NB * sizeof(double));
+        __syncwarp();
+        double* dst = stages + stage * STAGE_DOUBLES;
+        if (lane < KT) bulk_g2s(dst + lane * LDS_T, srcA + (int64_t)(c * KT + lane) * ldA, NB * sizeof(double), &full[stage]);
+        else bulk_g2s(dst + KT * LDS_T + (lane - KT) * LDS_T, srcB + (int64_t)(c * KT + lane - KT) * ldB, NB * sizeof(double), &full[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (tc.post) for (; rissued < NB / KT; ++rissued) issue_r(rissued);
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  // SMSP s = warp & 3 hosts warps {s, s+4}; pair column groups {0,3} / {1,2} on one SMSP so the
+  // triangular skips of the post-multiply balance across the four DMMA pipes.
+  const int s4 = warp & 3, h = warp >> 2;
+  const int wm = s4 & 1;
+  const int wn = (s4 >> 1) ? (1 + h) : (3 * h);
+  const int gq = lane >> 2, t = lane & 3;
+  const int row0 = wm * 64 + gq;  // + mi*8
+  const int col0 = wn * 32 + gq;  // + ni*8  (operand row index of B)
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  {
+    int stage = 0; uint32_t phase = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&full[stage], phase);
+      const double* As = stages + stage * STAGE_DOUBLES;
+      const double* Bs = As + KT * LDS_T;
+#pragma unroll
+      for (int k4 = 0; k4 < KT / 4; ++k4) {
+        double a[8], b[4];
+        const double* ap = As + (k4 * 4 + t) * LDS_T + row0;
+        const double* bp = Bs + (k4 * 4 + t) * LDS_T + col0;
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) a[mi] = ap[mi * 8];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+    }
+  }
+
+  // ---- T = Cin - acc (Cholesky) or acc
+  const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * NB;
+  if (tc.use_cin) {
+    const double* Cin = g.Cin + (int64_t)gp * g.mat_stride + grow + gcol * npad;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        acc[mi][ni][0] = Cin[r + (int64_t)cc * npad] - acc[mi][ni][0];
+        acc[mi][ni][1] = Cin[r + (int64_t)(cc + 1) * npad] - acc[mi][ni][1];
+      }
+  }
+
+  double* Cout = g.Cout + (int64_t)gp * g.mat_stride;
+  if (tc.post == 0) {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        Cout[grow + r + (gcol + cc) * npad] = acc[mi][ni][0];
+        Cout[grow + r + (gcol + cc + 1) * npad] = acc[mi][ni][1];
+        if (g.mode == GEMM_LAUUM && tc.i != tc.j) {  // mirror: full symmetric K^-1 for the gradient / predict stages
+          *reinterpret_cast<double2*>(&Cout[gcol + cc + (grow + r) * npad]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+      }
+    return;
+  }
+
+  // ---- post-multiply: park T in the (now idle) stage ring, then a second DMMA pass against Dinv chunks
+  named_bar_sync(1, N_CONSUMER_WARPS * 32);  // every consumer finished reading the ring
+  double* Ts = stages;
+  if (tc.post == 1) {  // A operand: Ts[k][m] = T[m][k]
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        Ts[cc * LDS_T + r] = acc[mi][ni][0];
+        Ts[(cc + 1) * LDS_T + r] = acc[mi][ni][1];
+      }
+  } else {  // B operand: Ts[k][n] = T[k][n]
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        *reinterpret_cast<double2*>(&Ts[r * LDS_T + cc]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      }
+  }
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  named_bar_sync(1, N_CONSUMER_WARPS * 32);
+
+  // Dinv is lower triangular: R[x][k] == 0 for k > x.  post 1: x = output column, post 2: x = output row.
+  const int kmax = (tc.post == 1) ? (wn * 32 + 31) : (wm * 64 + 63);
+  for (int c = 0; c < NB / KT; ++c) {
+    const int buf = c & 1;
+    mbar_wait(&rfull[buf], (c >> 1) & 1);
+    if (c * KT <= kmax) {
+      const double* Rs = rbuf + buf * RBUF_DOUBLES;
+#pragma unroll
+      for (int k4 = 0; k4 < KT / 4; ++k4) {
+        double a[8], b[4];
+        const double* ap = (tc.post == 1 ? Ts + (c * KT + k4 * 4 + t) * LDS_T : Rs + (k4 * 4 + t) * LDS_T) + row0;
+        const double* bp = (tc.post == 1 ? Rs + (k4 * 4 + t) * LDS_T : Ts + (c * KT + k4 * 4 + t) * LDS_T) + col0;
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) a[mi] = ap[mi * 8];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rempty[buf]);
+  }
+
+  if (tc.post == 1) {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        Cout[grow + r + (gcol + cc) * npad] = acc[mi][ni][0];
+        Cout[grow + r + (gcol + cc + 1) * npad] = acc[mi][ni][1];
+      }
+  } else {  // W(i,j) = -acc, stored transposed as V(j,i)
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        *reinterpret_cast<double2*>(&Cout[gcol + cc + (grow + r) * npad]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+      }
+  }
+}
+
+int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream) {
+  if (ntiles <= 0 || count <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tile_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_tile_gemm)", __FILE__, __LINE__);
+    configured = true;
+  }
+  dim3 grid(ntiles, count);
+  k_tile_gemm<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_tile_gemm launch", __FILE__, __LINE__);
+  return 0;
+}
+
+}  // namespace gprb

@@ -1,0 +1,13 @@
+"""Import shim: the product package lives in the directory ``gpr.jl_b200/`` (the name the build contract
+fixes); a dot is not importable, so this module loads it under the name ``gpr_jl_b200``."""
+import importlib.util as _ilu
+import os as _os
+import sys as _sys
+
+_pkg_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "gpr.jl_b200")
+_spec = _ilu.spec_from_file_location(
+    "gpr_jl_b200", _os.path.join(_pkg_dir, "__init__.py"), submodule_search_locations=[_pkg_dir]
+)
+_mod = _ilu.module_from_spec(_spec)
+_sys.modules["gpr_jl_b200"] = _mod
+_spec.loader.exec_module(_mod)

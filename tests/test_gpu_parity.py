@@ -1,0 +1,313 @@
+"""GPU parity: the CUDA path (through the C ABI, gpr.jl_b200) against the CPU oracle on identical inputs.
+
+Tolerances are the north_star's: kernel matrices 1e-12 relative, logML and gradient 1e-8 relative, predictive
+mean/variance 1e-9 relative - asserted on well-conditioned inputs (cond <~ 1e6); on the config.json-realistic
+hyper-parameters (cond up to ~1e10) two correct fp64 factorisations differ by ~cond*eps, so the bound there is
+conditioning-aware (SURVEY.md section 7 hard part 3)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as go
+from oracle.lbfgs_oracle import LBFGSOptions, lbfgs
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.npz")
+KIND = {"se": "SEArd", "mat12": "Mat12Ard", "mat32": "Mat32Ard", "mat52": "Mat52Ard"}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def build_batch(gprb, trials, thetas, kind="se", log_noise=None):
+    """trials: list of dict(X (d,n), Y (G,n)); thetas: list of (G,P) arrays."""
+    gps = []
+    K = getattr(gprb, KIND[kind])
+    for tr, th in zip(trials, thetas):
+        for k in range(tr["Y"].shape[0]):
+            t = th[k]
+            gps.append(gprb.GPE(tr["X"], tr["Y"][k], gprb.MeanZero(), K(t[1:-1], t[-1]), logNoise=t[0]))
+    return gprb.GPBatch(gps)
+
+
+def oracle_all(trials, thetas, kind="se", grad=True):
+    out = []
+    for tr, th in zip(trials, thetas):
+        X = np.ascontiguousarray(tr["X"].T)
+        for k in range(tr["Y"].shape[0]):
+            out.append(go.eval_mll(X, tr["Y"][k], th[k], kind=kind, with_grad=grad, return_state=True))
+    return out
+
+
+@pytest.mark.parametrize("system,n", [("P1", 256), ("P1", 100), ("P2", 300), ("CP", 257), ("FB", 128)])
+def test_eval_parity_well_conditioned(gprb, system, n):
+    from gpr_jl_b200 import data
+    tr = data.make_trial(system, n, seed=100 + n)
+    th = data.theta0(system, tr["X"])
+    th[1:-1] -= 1.0
+    G = tr["Y"].shape[0]
+    thetas = [np.tile(th, (G, 1)) + 0.05 * np.random.default_rng(n).standard_normal((G, th.size))]
+    batch = build_batch(gprb, [tr], thetas)
+    mll, grad, info = batch.eval(grad=True)
+    ref = oracle_all([tr], thetas)
+    for b, r in enumerate(ref):
+        assert info[b] == r["info"] == 0
+        K = batch.K(b)
+        assert rel(K, r["state"]["K"]) <= 1e-12
+        nz = r["state"]["K"] > 1e-290
+        assert np.max(np.abs(K[nz] - r["state"]["K"][nz]) / r["state"]["K"][nz]) <= 1e-12  # element-wise relative
+        assert abs(mll[b] - r["mll"]) <= 1e-8 * abs(r["mll"])
+        assert rel(grad[b], r["grad"]) <= 1e-8
+        assert rel(batch.alpha(b), r["state"]["alpha"]) <= 1e-8
+        assert rel(batch.chol_U(b), np.triu(r["state"]["U"])) <= 1e-10
+        assert rel(batch.Kinv(b), r["state"]["Kinv"]) <= 1e-8
+    # value-only evaluation returns the identical mll (same factorisation path)
+    mll2, g2, _ = batch.eval(grad=False)
+    assert g2 is None and np.array_equal(mll, mll2)
+
+
+def test_eval_parity_config_thetas_conditioning_aware(gprb):
+    """theta_0 from the reference's config.json (s_f ~ 300-450, cond(K) ~ 1e8-1e10)."""
+    from gpr_jl_b200 import data
+    for name, n in [("P1", 256), ("CP", 384)]:
+        tr = data.make_config(name, trials=1, n=n)[0]
+        batch = build_batch(gprb, [tr], [tr["theta0"]])
+        mll, grad, info = batch.eval(grad=True)
+        ref = oracle_all([tr], [tr["theta0"]])
+        for b, r in enumerate(ref):
+            cond = go.cond_estimate(r["state"]["K"])
+            tol = max(1e-8, 50 * cond * 2.2e-16)
+            assert info[b] == r["info"]
+            assert rel(batch.K(b), r["state"]["K"]) <= 1e-12
+            assert abs(mll[b] - r["mll"]) <= tol * abs(r["mll"]), (name, b, cond)
+            assert rel(grad[b], r["grad"]) <= tol, (name, b, cond, rel(grad[b], r["grad"]))
+
+
+def test_golden_vectors(gprb):
+    z = np.load(GOLD)
+    for nm in sorted({k.split("/")[0] for k in z.files}):
+        kind = str(z[f"{nm}/kind"])
+        tr = {"X": z[f"{nm}/X"], "Y": z[f"{nm}/Y"]}
+        G = tr["Y"].shape[0]
+        th = np.tile(z[f"{nm}/theta"], (G, 1))
+        batch = build_batch(gprb, [tr], [th], kind=kind)
+        mll, grad, info = batch.eval(grad=True)
+        assert np.array_equal(info, z[f"{nm}/info"])
+        tol = 1e-8 if "cfg" not in nm else 1e-6
+        np.testing.assert_allclose(mll, z[f"{nm}/mll"], rtol=tol)
+        for b in range(G):
+            assert rel(grad[b], z[f"{nm}/grad"][b]) <= tol, (nm, b)
+        mu, var = batch.predict_y(z[f"{nm}/Xtest"])
+        ptol = 1e-9 if "cfg" not in nm else 1e-6
+        assert rel(mu, z[f"{nm}/mu"]) <= ptol, nm
+        np.testing.assert_allclose(var, z[f"{nm}/var"], rtol=ptol, atol=1e-13)
+
+
+@pytest.mark.parametrize("kind", ["mat12", "mat32", "mat52"])
+def test_matern_kernels(gprb, kind):
+    from gpr_jl_b200 import data
+    tr = data.make_trial("P2", 200, seed=5)
+    th = data.theta0("P2", tr["X"])
+    th[1:-1] -= 1.0
+    thetas = [np.tile(th, (6, 1))]
+    batch = build_batch(gprb, [tr], thetas, kind=kind)
+    mll, grad, info = batch.eval()
+    for b, r in enumerate(oracle_all([tr], thetas, kind=kind)):
+        assert rel(batch.K(b), r["state"]["K"]) <= 1e-12
+        assert abs(mll[b] - r["mll"]) <= 1e-8 * abs(r["mll"])
+        assert rel(grad[b], r["grad"]) <= 1e-8
+
+
+def test_predict_parity_and_mean_only(gprb):
+    from gpr_jl_b200 import data
+    tr = data.make_trial("CP", 300, seed=9, n_test=21)
+    th = data.theta0("CP", tr["X"])
+    th[1:-1] -= 1.0
+    thetas = [np.tile(th, (4, 1))]
+    batch = build_batch(gprb, [tr], thetas)
+    batch.eval(grad=False)  # value-only state: predict must build the inverse itself
+    mu, var = batch.predict_y(tr["Xtest"])
+    mu2, none = batch.predict_y(tr["Xtest"], var=False)
+    assert none is None and np.array_equal(mu, mu2)
+    X = np.ascontiguousarray(tr["X"].T)
+    for b, r in enumerate(oracle_all([tr], thetas, grad=False)):
+        m_o, v_o = go.predict(X, th, r["state"], np.ascontiguousarray(tr["Xtest"].T))
+        assert rel(mu[b], m_o) <= 1e-9
+        np.testing.assert_allclose(var[b], v_o, rtol=1e-9, atol=1e-13)
+    # reference call pattern: one GP, one test column (predictdynamics.jl:13) -> (mu, s2), take [1][1]
+    gp = batch.gps[2]
+    m1, v1 = gprb.predict_y(gp, tr["Xtest"][:, 3:4])
+    assert m1.shape == (1,) and m1[0] == mu[2, 3] and v1[0] == var[2, 3]
+    # per-GP test blocks
+    blocks = [tr["Xtest"][:, b:b + 5] for b in range(4)]
+    mu3, var3 = batch.predict_y(blocks, per_gp=True)
+    for b in range(4):
+        np.testing.assert_allclose(mu3[b], mu[b, b:b + 5], rtol=1e-13)
+
+
+def test_mean_function_plugin(gprb):
+    """MeanDynamics-style host mean: only y - m(X) and m(x*) cross the boundary (src/mDynamics.jl:41-55)."""
+    from gpr_jl_b200 import data
+    tr = data.make_trial("P1", 90, seed=21, n_test=4)
+    th = data.theta0("P1", tr["X"])
+    calls = []
+
+    def nominal_step(x):  # stand-in for setstates! + newton!: a cheap nominal model of the next state
+        calls.append(1)
+        return 0.9 * np.asarray(x)
+
+    cache = gprb.MDCache()
+    from gpr_jl_b200.gp import getmu
+    gps = [gprb.GPE(tr["X"], tr["Y"][k], gprb.MeanDynamics(nominal_step, getmu([9, 10, 11]), k + 1, cache),
+                    gprb.SEArd(th[1:-1], th[-1])) for k in range(3)]
+    batch = gprb.GPBatch(gps)
+    mll, _, _ = batch.eval(grad=False)
+    X = np.ascontiguousarray(tr["X"].T)
+    for k in range(3):
+        m = 0.9 * tr["X"][8 + k]
+        r = go.eval_mll(X, tr["Y"][k] - m, th, with_grad=False, return_state=True)
+        assert abs(mll[k] - r["mll"]) <= 1e-8 * abs(r["mll"])
+    n_before = len(calls)
+    mu, _ = batch.predict_y(tr["Xtest"], var=False)
+    assert n_before == 90 and len(calls) - n_before == 4  # shared MDCache: one nominal step per column, not per GP
+    mu_o, _ = go.predict(X, th, go.eval_mll(X, tr["Y"][0] - 0.9 * tr["X"][8], th, with_grad=False, return_state=True)["state"],
+                         np.ascontiguousarray(tr["Xtest"].T), mstar=0.9 * tr["Xtest"][8], want_var=False)
+    assert rel(mu[0], mu_o) <= 1e-9
+
+
+def test_failure_codes_and_jitter(gprb):
+    from gpr_jl_b200 import data
+    tr = data.make_trial("P1", 64, seed=3)
+    tr["X"][:, 32:] = tr["X"][:, :32]  # exact duplicates -> K_f singular
+    tr["X"] = np.asfortranarray(tr["X"])
+    th = data.theta0("P1", tr["X"])
+    th[0] = -30.0  # no noise: Cholesky fails until make_posdef! adds jitter
+    thetas = np.tile(th, (3, 1))
+    thetas[1, 0] = -2.0          # healthy GP in the same batch
+    thetas[2, 4] = np.nan        # non-finite theta
+    batch = build_batch(gprb, [tr], [thetas])
+    mll, grad, info = batch.eval()
+    ref = oracle_all([tr], [thetas])
+    assert ref[0]["info"] >= 1 and 1 <= info[0] <= 10
+    assert abs(info[0] - ref[0]["info"]) <= 1  # borderline pivots may differ by one retry between LAPACK and the GPU
+    assert info[1] == 0 and abs(mll[1] - ref[1]["mll"]) <= 1e-8 * abs(ref[1]["mll"])
+    assert info[2] == -2 and mll[2] == -np.inf and np.all(np.isnan(grad[2]))
+    # a failed neighbour must not poison the batch
+    assert rel(grad[1], ref[1]["grad"]) <= 1e-8
+
+
+def test_active_mask(gprb):
+    from gpr_jl_b200 import data
+    tr = data.make_trial("P2", 140, seed=8)
+    th = data.theta0("P2", tr["X"])
+    thetas = np.tile(th, (6, 1))
+    batch = build_batch(gprb, [tr], [thetas])
+    mll0, g0, _ = batch.eval()
+    th2 = thetas + 0.3
+    act = np.array([1, 0, 1, 0, 0, 1], dtype=np.uint8)
+    mll1, g1, _ = batch.eval(theta=th2, active=act)
+    ref = oracle_all([tr], [th2])
+    for b in range(6):
+        if act[b]:
+            assert abs(mll1[b] - ref[b]["mll"]) <= 1e-8 * abs(ref[b]["mll"])
+        else:
+            assert np.isnan(mll1[b])  # untouched output
+            assert rel(batch.alpha(b), oracle_all([tr], [thetas])[b]["state"]["alpha"]) <= 1e-8  # state kept
+
+
+def test_multi_trial_batch_shares_datasets(gprb):
+    from gpr_jl_b200 import data
+    trials = data.make_config("CP", trials=3, n=200)
+    thetas = []
+    for tr in trials:
+        th = data.theta0("CP", tr["X"])
+        thetas.append(np.tile(th, (4, 1)))
+    batch = build_batch(gprb, trials, thetas)
+    assert batch.B == 12 and len(batch._ds) == 3
+    mll, grad, info = batch.eval()
+    for b, r in enumerate(oracle_all(trials, thetas)):
+        assert abs(mll[b] - r["mll"]) <= 1e-8 * abs(r["mll"])
+        assert rel(grad[b], r["grad"]) <= 1e-8
+
+
+def test_optimize_matches_scalar_oracle(gprb):
+    """Batched lock-step L-BFGS on the GPU vs the scalar Optim restatement with the CPU oracle objective, with a
+    deterministic iteration cap (the reference's time_limit is wall-clock)."""
+    from gpr_jl_b200 import data
+    tr = data.make_trial("P1", 96, seed=17)
+    th = data.theta0("P1", tr["X"])
+    thetas = np.tile(th, (3, 1))
+    batch = build_batch(gprb, [tr], [thetas])
+    res = batch.optimize(gprb.LBFGS(linesearch=gprb.BackTracking(order=2)), gprb.Options(iterations=12))
+    X = np.ascontiguousarray(tr["X"].T)
+    for k in range(3):
+        f = lambda t: -go.eval_mll(X, tr["Y"][k], t, with_grad=False)["mll"]
+        def fg(t):
+            r = go.eval_mll(X, tr["Y"][k], t)
+            return (-r["mll"], -r["grad"]) if r["info"] >= 0 else (np.inf, np.full(t.size, np.nan))
+        o = lbfgs(f, fg, th, LBFGSOptions(iterations=12))
+        assert res[k]["iterations"] == o.iterations
+        assert res[k]["minimum"] <= f(th)  # improved on the start point
+        assert abs(res[k]["minimum"] - o.f) <= 1e-6 * abs(o.f), (k, res[k]["minimum"], o.f)
+        assert batch.gps[k].mll == -res[k]["minimum"]
+    # state after optimize! is evaluated at the minimiser: predict works right away
+    mu, var = batch.predict_y(tr["X"][:, :3])
+    assert np.all(np.isfinite(mu)) and np.all(var > 0)
+
+
+def test_reference_call_sequence_single_gp(gprb):
+    """The literal per-GP sequence of CPnoise.jl:38-41 + predictdynamics.jl:13."""
+    from gpr_jl_b200 import data
+    tr = data.make_trial("CP", 128, seed=31, n_test=2)
+    params = np.exp(np.concatenate([[0.0], data.theta0("CP", tr["X"])[1:-1]]))  # [s_f, l_1..l_d] like config.json
+    kernel = gprb.SEArd(np.log(params[1:]), np.log(params[0]))
+    gp = gprb.GP(tr["X"], tr["Y"][0], gprb.MeanZero(), kernel)
+    assert np.isfinite(gp.mll) and gp.logNoise == -2.0
+    r = gprb.optimize(gp, gprb.LBFGS(linesearch=gprb.BackTracking(order=2)), gprb.Options(iterations=5))
+    assert r["iterations"] <= 5 and -r["minimum"] >= gp.mll - 1e-9
+    obs = tr["Xtest"][:, 0].reshape(-1, 1)
+    mu = gprb.predict_y(gp, obs)[0][0]
+    assert np.isfinite(mu)
+
+
+def test_full_size_properties_n2000(gprb):
+    """BASELINE size (n=2000, d=26): size-independent properties instead of a full oracle run."""
+    from gpr_jl_b200 import data
+    tr = data.make_config("CP", trials=1)[0]
+    assert tr["X"].shape == (26, 2000)
+    th = data.theta0("CP", tr["X"])
+    th[1:-1] -= 0.5
+    thetas = np.tile(th, (4, 1))
+    batch = build_batch(gprb, [tr], [thetas])
+    mll, grad, info = batch.eval()
+    assert np.all(info == 0)
+    X = np.ascontiguousarray(tr["X"].T)
+    K = go.assemble_K(X, th)
+    assert rel(batch.K(0), K) <= 1e-12
+    for b in (0, 3):
+        a = batch.alpha(b)
+        assert np.max(np.abs(K @ a - tr["Y"][b])) <= 1e-8 * np.max(np.abs(tr["Y"][b]))  # K alpha = y
+        U = batch.chol_U(b)
+        cols = [0, 777, 1999]
+        assert np.max(np.abs((U.T @ U[:, cols]) - K[:, cols])) <= 1e-10 * np.max(np.abs(K))
+        Ki = batch.Kinv(b)
+        E = K @ Ki[:, cols]
+        E[cols, range(3)] -= 1.0
+        assert np.max(np.abs(E)) <= 1e-7
+        assert np.allclose(Ki, Ki.T, rtol=0, atol=1e-9 * np.max(np.abs(Ki)))
+    # oracle value (one LAPACK evaluation at n=2000 takes a few seconds) and a directional finite difference
+    r = go.eval_mll(X, tr["Y"][1], th, with_grad=True)
+    assert abs(mll[1] - r["mll"]) <= 1e-8 * abs(r["mll"])
+    assert rel(grad[1], r["grad"]) <= 1e-8
+    v = np.random.default_rng(0).standard_normal(th.size)
+    v /= np.linalg.norm(v)
+    h = 1e-5
+    mp, _, _ = batch.eval(theta=thetas + h * v, grad=False)
+    mm, _, _ = batch.eval(theta=thetas - h * v, grad=False)
+    fd = (mp - mm) / (2 * h)
+    for b in range(4):
+        assert abs(fd[b] - grad[b] @ v) <= 1e-5 * max(1.0, abs(grad[b] @ v))
