@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py - headline metric of BASELINE.json on B200: batched fp64 logML+gradient evaluations/s at n=2000.
+
+Workload (config.workload): the CP cartpole noise experiment shape - n=2000 training states, d=26 (two bodies x 13
+CState entries), G=4 output GPs per trial, 100 trial datasets -> B=400 independent GPs per GPU.  One *step* = one
+logML+gradient evaluation of all B GPs (assembly -> Cholesky -> solve -> inverse -> fused gradient), at a fresh theta
+per step (theta_0 + seeded perturbations).  Multi-GPU (torchrun): every rank owns its own 100 trials (weak scaling,
+no data-path collective) and a per-step NCCL all-gather of the per-GP results stands in for the reference's result
+callbacks (examples/parallel/core.jl:47-56).
+
+  value  : inputs (X, y, theta) resident in HBM before the timed region (gprb_eval_device), CUDA events, max over ranks
+  e2e    : the public API call GPBatch.eval() with HOST buffers; every step re-uploads X, y and theta and reads
+           mll + grad back (host<->device copies inside the timed region)
+  roofline: the DMMA tile-GEMM kernel (k_tile_gemm), algorithmic n^3 flops per evaluation / summed launch time
+  cpu_baseline / --impl reference: the oracle (restated reference path, scipy OpenBLAS) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAIN, TRIALS, SYSTEM = 2000, 100, "CP"
+METRIC = "batched fp64 logML+gradient evals/sec (n=2000)"
+
+
+def flops_eval(n, d):  # minimal algorithm, value+gradient
+    return n ** 3 + 4 * d * n ** 2 + 4 * n ** 2
+
+
+def fp64_peak():
+    """FP64 denominator: MEASURED_PEAKS.json has no fp64 figure, so the cuBLAS DGEMM 8192^3 measurement taken on this
+    pool's B200 with tools/measure_fp64_peak.py (committed as profiles/FP64_PEAKS.json) is used."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAKS.json")))
+        return float(p["dgemm_tflops_sustained"]), "profiles/FP64_PEAKS.json (cuBLAS DGEMM 8192^3 sustained, measured on this pool)"
+    except Exception:
+        return 37.0, "nominal fallback (40 TF/s spec; no measurement file)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_eval_rate(seconds_budget, n_max_evals, threads):
+    """Oracle (restated reference path) logML+gradient evaluations/s on the host cores, bounded sample."""
+    from oracle import gp_oracle as go
+    import gpr_jl_b200  # noqa: F401
+    from gpr_jl_b200 import data
+    tr = data.make_config(SYSTEM, trials=1)[0]
+    X = np.ascontiguousarray(tr["X"].T)
+    thetas = data.perturbed_thetas(tr["theta0"][0], n_max_evals, seed=7)
+    t0 = time.time()
+    k = 0
+    while k < n_max_evals and (k == 0 or time.time() - t0 < seconds_budget):
+        go.eval_mll(X, tr["Y"][k % tr["Y"].shape[0]], thetas[k], with_grad=True)
+        k += 1
+    dt = time.time() - t0
+    return k / dt, k, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count()
+    # W warm-up + K timed "steps", each step one bounded sample (1 evaluation of the n=2000 CP workload)
+    from oracle import gp_oracle as go
+    import gpr_jl_b200  # noqa: F401
+    from gpr_jl_b200 import data
+    tr = data.make_config(SYSTEM, trials=1)[0]
+    X = np.ascontiguousarray(tr["X"].T)
+    thetas = data.perturbed_thetas(tr["theta0"][0], args.steps + args.warmup, seed=7)
+    for w in range(args.warmup):
+        go.eval_mll(X, tr["Y"][w % 4], thetas[w], with_grad=True)
+    t0 = time.time()
+    for k in range(args.steps):
+        go.eval_mll(X, tr["Y"][k % 4], thetas[args.warmup + k], with_grad=True)
+    dt = time.time() - t0
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "CP cartpole noise experiment, n=2000, d=26, G=4 GPs/trial, 100 trials (B=400 GPs per GPU)",
+                       "sample": "1 logML+gradient evaluation of one GP per step"},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} evaluations of one n=2000,d=26 GP (oracle: restated GaussianProcesses.jl path on scipy OpenBLAS; Julia absent)"},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trials", type=int, default=TRIALS, help="trial datasets per GPU (default: the full 100)")
+    ap.add_argument("--n", type=int, default=N_TRAIN)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-predict", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import gpr_jl_b200 as G
+    from gpr_jl_b200 import data
+
+    n, T = args.n, args.trials
+    trials = data.make_config(SYSTEM, trials=T, n=n, first_trial=rank * T)
+    d = trials[0]["X"].shape[0]
+    gps = []
+    for tr in trials:
+        for k in range(tr["Y"].shape[0]):
+            th = tr["theta0"][k]
+            gps.append(G.GPE(tr["X"], tr["Y"][k], G.MeanZero(), G.SEArd(th[1:-1], th[-1]), logNoise=th[0]))
+    batch = G.GPBatch(gps)
+    B, P = batch.B, batch.P
+    theta0 = batch.get_params()
+    nsets = args.steps + args.warmup
+    thetas = data.perturbed_thetas(theta0, nsets, seed=1234 + rank)
+
+    dev = torch.device("cuda", local)
+    th_dev = [torch.from_numpy(np.ascontiguousarray(t)).to(dev) for t in thetas]
+    mll_dev = torch.empty(B, dtype=torch.float64, device=dev)
+    grad_dev = torch.empty(B, P, dtype=torch.float64, device=dev)
+    info_dev = torch.empty(B, dtype=torch.int32, device=dev)
+    gathered = [torch.empty(B, P + 1, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step_device(i):
+        batch.eval_device(th_dev[i].data_ptr(), mll_dev.data_ptr(), grad_dev.data_ptr(), info_dev.data_ptr(), stream.cuda_stream)
+        if world > 1:  # final gather of per-GP results over NVLink (latency-bound, a few hundred KB)
+            dist.all_gather(gathered, torch.cat([mll_dev[:, None], grad_dev], dim=1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = G.gp.context()
+    for w in range(args.warmup):
+        step_device(w)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step_device(args.warmup + k)
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    sampler.stop_flag = True
+    info_ok = int((info_dev >= 0).sum().item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: public API with host buffers; X, y, theta go up and mll, grad come back every step
+    Xs = [tr["X"] for tr in trials]
+    ymm = batch.ymm.copy()
+    def step_host(i):
+        batch.update_data(Xs, ymm)
+        return batch.eval(theta=thetas[i], grad=True)
+    step_host(0)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        mll_h, grad_h, info_h = step_host(args.warmup + k)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(dt.item())
+    h2d = T * d * n * 8 + B * n * 8 + B * P * 8
+    d2h = B * 8 + B * P * 8 + B * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0, profiled pass: single stream, events around every GEMM launch)
+    batch.set_profiling(True)
+    batch.eval_device(th_dev[0].data_ptr(), mll_dev.data_ptr(), grad_dev.data_ptr(), info_dev.data_ptr(), stream.cuda_stream)
+    batch.eval_device(th_dev[1].data_ptr(), mll_dev.data_ptr(), grad_dev.data_ptr(), info_dev.data_ptr(), stream.cuda_stream)
+    st = batch.last_stage_ms()
+    batch.set_profiling(False)
+    peak, peak_src = fp64_peak()
+    gemm_flops = float(B) * n ** 3  # potrf n^3/3 + inverse-from-factor 2n^3/3 (algorithmic, un-padded)
+    achieved = gemm_flops / (st["gemm"] * 1e-3) / 1e12 if st["gemm"] > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "k_tile_gemm (fp64 DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "launches_per_step": int(st["gemm_launches"]), "flops_per_launch": gemm_flops / max(st["gemm_launches"], 1),
+            "avg_launch_ms": st["gemm"] / max(st["gemm_launches"], 1),
+            "stage_ms": {k: round(v, 3) for k, v in st.items() if k != "gemm_launches"},
+            "whole_eval_frac_of_peak": (flops_eval(n, d) * B * args.steps / (ms_total * 1e-3) / 1e12) / peak}
+
+    # ---- prediction throughput (second half of the BASELINE metric): 100 test states per GP, mean + variance
+    pred = None
+    if not args.no_predict:
+        m = 100
+        Xt = data.make_trial(SYSTEM, 8, seed=99, n_test=m)["Xtest"]
+        batch.predict_y(Xt, var=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            batch.predict_y(Xt, var=True)
+        tp = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            batch.predict_y(Xt, var=False)
+        tm = (time.perf_counter() - t0) / reps
+        pred = {"samples_per_s_mean_var": B * m / tp, "samples_per_s_mean_only": B * m / tm, "m": m, "B": B,
+                "note": "through gprb_predict with host buffers (e2e), one GPU"}
+
+    cpu_v, cpu_k, cpu_dt = cpu_eval_rate(args.cpu_seconds, 6, os.cpu_count()) if world == 1 else (None, 0, 0)
+    line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"CP cartpole noise experiment, n={n}, d={d}, G=4 GPs/trial, {T} trials (B={B} GPs per GPU)",
+                       "evals_per_step": world * B, "theta": "config.json CP_MAX2048 + 0.1*N(0,I), fresh per step",
+                       "l2": f"working set {2 * B * batch.n * batch.n * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
+                       "info_ok": info_ok, "parallelism": f"trial-sharded x{world}, per-step NCCL all-gather of results"},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+    if cpu_v is not None:
+        line["cpu_baseline"] = {"value": cpu_v, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{cpu_k} logML+gradient evaluations of one n={N_TRAIN},d=26 GP in {cpu_dt:.1f} s (oracle: restated GaussianProcesses.jl path, scipy OpenBLAS all cores)"}
+    if pred:
+        line["predict"] = pred
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,7 @@ static void free_batch(gprb_batch* b) {
   }
   for (int s = 0; s < 8; ++s)
     if (b->ev[s]) cudaEventDestroy(b->ev[s]);
+  for (cudaEvent_t e : b->gemm_ev) cudaEventDestroy(e);
   delete b;
 }
 
@@ -59,7 +60,20 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
   const int64_t ms = b->npad * b->npad, dstride = (int64_t)J * NB * NB;
   int rc;
   int64_t& launches = b->ctx->launches;
-  if (prof) cudaEventRecord(b->ev[0], st);
+  auto gemm = [&](const GemmArgs& a, int ntiles) -> int {
+    if (!prof) return launch_tile_gemm(a, ntiles, count, st);
+    while ((int)b->gemm_ev.size() < b->gemm_ev_used + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
+      b->gemm_ev.push_back(e);
+    }
+    cudaEventRecord(b->gemm_ev[b->gemm_ev_used], st);
+    int r = launch_tile_gemm(a, ntiles, count, st);
+    cudaEventRecord(b->gemm_ev[b->gemm_ev_used + 1], st);
+    b->gemm_ev_used += 2;
+    return r;
+  };
+  if (prof) { b->gemm_ev_used = 0; cudaEventRecord(b->ev[0], st); }
   AssembleArgs aa{b->Xtptr, b->theta, b->jitter, b->A, b->fail, list, ms, (int)b->n, (int)b->npad, b->d, J, b->kind};
   if ((rc = launch_assemble(aa, count, st))) return rc;
   ++launches;
@@ -68,13 +82,13 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
   DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0};
   for (int j = 0; j < J; ++j) {
     ga.step = j; ga.mode = GEMM_CHOL_DIAG;
-    if ((rc = launch_tile_gemm(ga, 1, count, st))) return rc;
+    if ((rc = gemm(ga, 1))) return rc;
     da.step = j;
     if ((rc = launch_diag_factor(da, count, st))) return rc;
     launches += 2;
     if (j + 1 < J) {
       ga.mode = GEMM_CHOL_COL;
-      if ((rc = launch_tile_gemm(ga, J - 1 - j, count, st))) return rc;
+      if ((rc = gemm(ga, J - 1 - j))) return rc;
       ++launches;
     }
   }
@@ -88,11 +102,11 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
     ga.Cin = nullptr;
     for (int i = 1; i < J; ++i) {
       ga.step = i; ga.mode = GEMM_TRTRI_ROW; ga.Cout = b->Lm;
-      if ((rc = launch_tile_gemm(ga, i, count, st))) return rc;
+      if ((rc = gemm(ga, i))) return rc;
       ++launches;
     }
     ga.mode = GEMM_LAUUM; ga.step = 0; ga.Cout = b->A;
-    if ((rc = launch_tile_gemm(ga, J * (J + 1) / 2, count, st))) return rc;
+    if ((rc = gemm(ga, J * (J + 1) / 2))) return rc;
     ++launches;
     if (prof) cudaEventRecord(b->ev[4], st);
     GradArgs gr{b->Xtptr, b->theta, b->A, b->alpha, b->grad_part, b->grad, b->fail, list, ms,
@@ -121,6 +135,13 @@ static int run_pipeline(gprb_batch* b, int count, bool with_grad) {
       }
       GPRB_CUDA(cudaEventElapsedTime(&ms, b->ev[0], b->ev[last]));
       b->stage_ms[5] = ms;
+      double gsum = 0.0;
+      for (int k = 0; k + 1 < b->gemm_ev_used; k += 2) {
+        GPRB_CUDA(cudaEventElapsedTime(&ms, b->gemm_ev[k], b->gemm_ev[k + 1]));
+        gsum += ms;
+      }
+      b->stage_ms[6] = gsum;
+      b->stage_ms[7] = b->gemm_ev_used / 2;
     }
     return 0;
   }
@@ -169,6 +190,7 @@ static int evaluate_active(gprb_batch* b, int count, bool with_grad, std::vector
       else { tries[gp]++; again.push_back(gp); ++nretry; continue; }
       b->state_ok[gp] = info[gp] >= 0;
       b->inv_ok[gp] = with_grad && info[gp] >= 0;
+      b->v_ok[gp] = b->inv_ok[gp];
     }
     if (nretry == 0) break;
     for (int k = 0; k < nretry; ++k) b->list_host[k] = again[k];
@@ -288,6 +310,7 @@ static int upload_targets(gprb_batch* b, const double* ymm) {
   GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
   b->state_ok.assign(b->B, 0);
   b->inv_ok.assign(b->B, 0);
+  b->v_ok.assign(b->B, 0);
   return 0;
 }
 
@@ -372,9 +395,9 @@ int gprb_set_profiling(gprb_batch* b, int32_t on) {
   return GPRB_OK;
 }
 
-int gprb_last_stage_ms(gprb_batch* b, double out[6]) {
+int gprb_last_stage_ms(gprb_batch* b, double out[8]) {
   GPRB_REQUIRE(b && out, "gprb_last_stage_ms: NULL argument");
-  for (int i = 0; i < 6; ++i) out[i] = b->stage_ms[i];
+  for (int i = 0; i < 8; ++i) out[i] = b->stage_ms[i];
   return GPRB_OK;
 }
 
@@ -455,9 +478,9 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
   int ninv = 0;
   if (var)
     for (int i = 0; i < B; ++i)
-      if (!b->inv_ok[i]) b->list_host[ninv++] = i;
+      if (!b->v_ok[i]) b->list_host[ninv++] = i;
   if (ninv > 0) {
-    // variance needs K^-1: run the inverse stage (TRTRI rows + LAUUM) on the resident factors that lack it
+    // variance needs L^-1: run the TRTRI rows on the resident factors that lack it
     int rc = upload_list(b, ninv);
     if (rc) return rc;
     const int J = b->J;
@@ -468,10 +491,7 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
       if ((rc = launch_tile_gemm(ga, i, ninv, st))) return rc;
       b->ctx->launches++;
     }
-    ga.mode = GEMM_LAUUM; ga.step = 0; ga.Cout = b->A;
-    if ((rc = launch_tile_gemm(ga, J * (J + 1) / 2, ninv, st))) return rc;
-    b->ctx->launches++;
-    for (int k = 0; k < ninv; ++k) b->inv_ok[b->list_host[k]] = 1;
+    for (int k = 0; k < ninv; ++k) b->v_ok[b->list_host[k]] = 1;
   }
   const size_t nx = (size_t)(xstar_stride ? xstar_stride * (B - 1) + m * b->d : m * b->d);
   double *dX = nullptr, *dms = nullptr, *dmu = nullptr, *dvar = nullptr;
@@ -483,8 +503,8 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
     cudaError_t e;
     if ((e = cudaMemcpyAsync(dX, Xstar, sizeof(double) * nx, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D Xstar", __FILE__, __LINE__); break; }
     if (mstar && (e = cudaMemcpyAsync(dms, mstar, sizeof(double) * B * m, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D mstar", __FILE__, __LINE__); break; }
-    PredictArgs pa{b->Xptr, b->theta, b->alpha, var ? b->A : nullptr, dX, dms, dmu, dvar, xstar_stride,
-                   b->npad * b->npad, (int)b->n, (int)b->npad, b->d, (int)m, b->kind};
+    PredictArgs pa{b->Xptr, b->theta, b->alpha, b->Lm, b->DinvT, dX, dms, dmu, dvar, xstar_stride,
+                   b->npad * b->npad, (int64_t)b->J * NB * NB, (int)b->n, (int)b->npad, b->d, (int)m, b->kind};
     if ((rc = launch_predict(pa, B, st))) break;
     b->ctx->launches++;
     if ((e = cudaMemcpyAsync(mu, dmu, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H mu", __FILE__, __LINE__); break; }

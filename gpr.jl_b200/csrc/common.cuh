@@ -92,7 +92,10 @@ struct gprb_batch {
   bool profiling = false;
   std::vector<uint8_t> state_ok;  // per GP: factor + alpha resident (last evaluation succeeded)
   std::vector<uint8_t> inv_ok;    // per GP: K^-1 resident in A (last evaluation was value+gradient)
-  double stage_ms[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<uint8_t> v_ok;      // per GP: V = L^-T resident in the upper tiles of Lm (TRTRI stage done)
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<cudaEvent_t> gemm_ev;  // profiling: start/stop pairs around every tile-GEMM launch
+  int gemm_ev_used = 0;
 };
 
 // --------------------------------------------------------------------------------------

@@ -87,12 +87,13 @@ struct PredictArgs {
   const double* const* X;  // [B] original d x n inputs
   const double* theta;
   const double* alpha;
-  const double* Kinv;      // nullptr => mean only
+  const double* Lm;        // V = L^-T in the strictly-upper tiles (variance only)
+  const double* DinvT;     // transposed inverse diagonal blocks
   const double* Xstar;     // d x m (+ b * xstar_stride)
   const double* mstar;     // [B][m] or nullptr
   double* mu;              // [B][m]
   double* var;             // [B][m] or nullptr
-  int64_t xstar_stride, mat_stride;
+  int64_t xstar_stride, mat_stride, dinv_stride;
   int n, npad, d, m, kind;
 };
 int launch_predict(const PredictArgs& a, int B, cudaStream_t stream);

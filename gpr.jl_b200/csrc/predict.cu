@@ -1,7 +1,7 @@
 // K6 posterior prediction (reference call examples/utils/predictdynamics.jl:13):
-//   k*_r = k(X[:,r], x*) ;  mu* = m(x*) + k*' alpha ;  var* = max(s_f^2 - k*' K^-1 k*, 0) + exp(2 logNoise)
+//   k*_r = k(X[:,r], x*) ;  mu* = m(x*) + k*' alpha ;  var* = max(s_f^2 - |L^-1 k*|^2, 0) + exp(2 logNoise)
 // One CTA handles PS test columns of one GP: cross-covariances are built once into shared memory, the mean is
-// a fused dot product, and the variance streams K^-1 once per CTA (8 test columns share every matrix element).
+// a fused dot product, and the variance streams the triangular inverse once per CTA (8 test columns share every element).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -89,40 +89,43 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
   }
   if (g.var == nullptr) return;
   __syncthreads();
-  // quadratic form q_s = sum_r k_r (sum_c Kinv[r][c] k_c): thread owns rows, streams columns (coalesced over rows)
-  const double* Kinv = g.Kinv + (int64_t)gp * g.mat_stride;
+  // latent variance through the factor, like the reference's whiten! (PDMats): v = L^-1 k*, var_f = s_f^2 - |v|^2.
+  // L^-1 is resident as V = L^-T (strictly-upper tiles of Lm, column r of V = row r of L^-1, contiguous) plus the
+  // transposed inverse diagonal blocks DinvT.  Warp per row, lanes over the contiguous column index.
+  const double* V = g.Lm + (int64_t)gp * g.mat_stride;
+  const double* DT = g.DinvT + (int64_t)gp * g.dinv_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double q[PS];
 #pragma unroll
   for (int s = 0; s < PS; ++s) q[s] = 0.0;
-  for (int r = threadIdx.x; r < n; r += PRED_THREADS) {
+  for (int r = warp; r < n; r += PRED_THREADS / 32) {
+    const int jb = r / NB, rl = r - jb * NB;
     double t[PS];
 #pragma unroll
     for (int s = 0; s < PS; ++s) t[s] = 0.0;
-    const double* Kr = Kinv + r;
-    int c = 0;
-    for (; c + 3 < n; c += 4) {
-      const double k0 = Kr[(int64_t)c * npad], k1 = Kr[(int64_t)(c + 1) * npad];
-      const double k2 = Kr[(int64_t)(c + 2) * npad], k3 = Kr[(int64_t)(c + 3) * npad];
+    const double* Vr = V + (int64_t)r * npad;
+    for (int c = lane; c < jb * NB; c += 32) {
+      const double v = Vr[c];
 #pragma unroll
-      for (int s = 0; s < PS; ++s) {
-        const double* kc = ks + (size_t)s * npad + c;
-        t[s] = fma(k0, kc[0], t[s]);
-        t[s] = fma(k1, kc[1], t[s]);
-        t[s] = fma(k2, kc[2], t[s]);
-        t[s] = fma(k3, kc[3], t[s]);
-      }
+      for (int s = 0; s < PS; ++s) t[s] = fma(v, ks[(size_t)s * npad + c], t[s]);
     }
-    for (; c < n; ++c) {
-      const double k0 = Kr[(int64_t)c * npad];
+    const double* Dr = DT + (int64_t)jb * NB * NB + (int64_t)rl * NB;  // DinvT(c, rl) = inv(L_jj)(rl, c), c <= rl
+    for (int c = lane; c <= rl; c += 32) {
+      const double v = Dr[c];
 #pragma unroll
-      for (int s = 0; s < PS; ++s) t[s] = fma(k0, ks[(size_t)s * npad + c], t[s]);
+      for (int s = 0; s < PS; ++s) t[s] = fma(v, ks[(size_t)s * npad + jb * NB + c], t[s]);
     }
 #pragma unroll
-    for (int s = 0; s < PS; ++s) q[s] = fma(ks[(size_t)s * npad + r], t[s], q[s]);
+    for (int s = 0; s < PS; ++s) {
+      double v = t[s];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      q[s] = fma(v, v, q[s]);
+    }
   }
   const double sn2 = exp(2.0 * th[0]);
   for (int s = 0; s < PS; ++s) {
-    const double tot = block_sum(q[s], red);
+    const double tot = block_sum(lane == 0 ? q[s] : 0.0, red);
     if (threadIdx.x == 0 && s < ns) g.var[(int64_t)gp * g.m + s0 + s] = fmax(sf2 - tot, 0.0) + sn2;
   }
 }

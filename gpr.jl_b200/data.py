@@ -37,8 +37,9 @@ _GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 
 
 def _body_state(phi, psi, offset):
-    """13-vector of one pendulum-like body at angle phi, rate psi."""
-    s = np.zeros(13)
+    """(13, m) block of one pendulum-like body at angles phi (m,), rates psi (m,)."""
+    phi = np.asarray(phi, dtype=np.float64)
+    s = np.zeros((13, phi.size))
     s[1] = 0.5 * np.sin(phi) + offset
     s[2] = -0.5 * np.cos(phi)
     s[3] = np.cos(phi / 2)
@@ -50,7 +51,8 @@ def _body_state(phi, psi, offset):
 
 
 def _cart_state(u, udot):
-    s = np.zeros(13)
+    u = np.asarray(u, dtype=np.float64)
+    s = np.zeros((13, u.size))
     s[1] = u
     s[3] = 1.0
     s[8] = udot
@@ -76,17 +78,15 @@ def make_trial(system: str, n: int, seed: int, noise: float = 1e-3, n_test: int 
             u = rng.uniform(-1, 1, tot)
             ud = rng.uniform(-1, 1, tot)
             force = rng.uniform(-1, 1, tot)
-            for i in range(tot):
-                X[13 * b:13 * b + 13, i] = _cart_state(u[i], ud[i])
-                ud2 = ud[i] + DT * force[i]
-                Xn[13 * b:13 * b + 13, i] = _cart_state(u[i] + DT * ud2, ud2)
+            X[13 * b:13 * b + 13] = _cart_state(u, ud)
+            ud2 = ud + DT * force
+            Xn[13 * b:13 * b + 13] = _cart_state(u + DT * ud2, ud2)
         else:
             phi = rng.uniform(-np.pi, np.pi, tot)
             psi = rng.uniform(-1, 1, tot) * 3.0
-            for i in range(tot):
-                X[13 * b:13 * b + 13, i] = _body_state(phi[i], psi[i], 0.25 * b)
-                p2, s2 = _step(phi[i], psi[i])
-                Xn[13 * b:13 * b + 13, i] = _body_state(p2, s2, 0.25 * b)
+            X[13 * b:13 * b + 13] = _body_state(phi, psi, 0.25 * b)
+            p2, s2 = _step(phi, psi)
+            Xn[13 * b:13 * b + 13] = _body_state(p2, s2, 0.25 * b)
     varying = np.abs(X).max(axis=1) > 0
     varying &= X.std(axis=1) > 0
     X = X + noise * rng.standard_normal(X.shape) * varying[:, None]  # noise only on the non-constant rows

@@ -365,6 +365,25 @@ class GPBatch:
                 gp.dmll = g[b].copy() if grad else None
         return mll, g, info
 
+    def eval_device(self, theta_ptr, mll_ptr, grad_ptr=None, info_ptr=None, stream=0):
+        """gprb_eval_device: theta (B,P) / mll (B,) / grad (B,P) / info (B,) are raw device pointers (ints, e.g.
+        ``torch.Tensor.data_ptr()``); no payload crosses PCIe.  Ordered after ``stream`` (a cudaStream_t handle)."""
+        self.lib.check(self.lib.dll.gprb_eval_device(self.handle, C.c_void_p(theta_ptr), C.c_void_p(mll_ptr),
+                                                     C.c_void_p(grad_ptr) if grad_ptr else None,
+                                                     C.c_void_p(info_ptr) if info_ptr else None, C.c_void_p(stream)))
+
+    def update_data(self, trials_X=None, ymm=None):
+        """Re-upload inputs into the resident allocations: ``trials_X`` = list of new d x n arrays, one per distinct
+        dataset in creation order; ``ymm`` (B, n) new targets (y - m(X))."""
+        if trials_X is not None:
+            for h, Xn in zip(self._ds.values(), trials_X):
+                Xc = as_f64(np.asarray(Xn).T)
+                self.lib.check(self.lib.dll.gprb_dataset_update(h, _d(Xc), self.d))
+        if ymm is not None:
+            ymm = as_f64(ymm).reshape(self.B, self.n)
+            self.lib.check(self.lib.dll.gprb_batch_set_targets(self.handle, _d(ymm)))
+            self.ymm = ymm
+
     def update_mll(self):
         return self.eval(grad=False)
 
@@ -447,9 +466,9 @@ class GPBatch:
         self.lib.check(self.lib.dll.gprb_set_profiling(self.handle, 1 if on else 0))
 
     def last_stage_ms(self):
-        out = np.zeros(6)
+        out = np.zeros(8)
         self.lib.check(self.lib.dll.gprb_last_stage_ms(self.handle, _d(out)))
-        return dict(zip(["assembly", "cholesky", "solve", "inverse", "gradient", "total"], out.tolist()))
+        return dict(zip(["assembly", "cholesky", "solve", "inverse", "gradient", "total", "gemm", "gemm_launches"], out.tolist()))
 
 
 def optimize(gp, method: LBFGS | None = None, options: Options | None = None):

@@ -141,10 +141,11 @@ int gprb_get_Kinv(gprb_batch* batch, int32_t b, double* out /* n x n symmetric; 
 
 /* ---- timing hooks for bench.py (CUDA events on the library's own streams) -------------- */
 /* Per-stage device time of the most recent gprb_eval / gprb_eval_device, milliseconds:
- * out[0]=assembly out[1]=cholesky out[2]=solve+mll out[3]=inverse out[4]=gradient out[5]=total.
- * Valid only when profiling was enabled with gprb_set_profiling(batch, 1) (serialises the stages). */
+ * out[0]=assembly out[1]=cholesky out[2]=solve+mll out[3]=inverse out[4]=gradient out[5]=total
+ * out[6]=sum over the DMMA tile-GEMM launches alone, out[7]=number of those launches.
+ * Valid only when profiling was enabled with gprb_set_profiling(batch, 1) (single stream, stages serialised). */
 int gprb_set_profiling(gprb_batch* batch, int32_t on);
-int gprb_last_stage_ms(gprb_batch* batch, double out[6]);
+int gprb_last_stage_ms(gprb_batch* batch, double out[8]);
 /* Number of kernel launches issued by the library since the context was created. */
 int64_t gprb_launch_count(gprb_ctx* ctx);
 
