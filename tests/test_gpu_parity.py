@@ -185,19 +185,30 @@ def test_failure_codes_and_jitter(gprb):
     tr["X"][:, 32:] = tr["X"][:, :32]  # exact duplicates -> K_f singular
     tr["X"] = np.asfortranarray(tr["X"])
     th = data.theta0("P1", tr["X"])
-    th[0] = -30.0  # no noise: Cholesky fails until make_posdef! adds jitter
+    th[0] = -30.0           # no noise ...
+    th[-1] = np.log(1e4)    # ... and s_f^2 = 1e8: the 32 duplicate pivots are pure rounding noise of size ~1e-8, so the
+    #                         first factorisation fails on any fp64 implementation; one jitter (1e-6*tr/n = 100) fixes it
     thetas = np.tile(th, (3, 1))
     thetas[1, 0] = -2.0          # healthy GP in the same batch
+    thetas[1, -1] = 0.0
     thetas[2, 4] = np.nan        # non-finite theta
     batch = build_batch(gprb, [tr], [thetas])
     mll, grad, info = batch.eval()
     ref = oracle_all([tr], [thetas])
-    assert ref[0]["info"] >= 1 and 1 <= info[0] <= 10
-    assert abs(info[0] - ref[0]["info"]) <= 1  # borderline pivots may differ by one retry between LAPACK and the GPU
+    assert ref[0]["info"] == 1 and info[0] == 1
+    assert abs(mll[0] - ref[0]["mll"]) <= 1e-6 * abs(ref[0]["mll"])
+    Kj = batch.K(0)  # the tap returns the jittered matrix that was factorised
+    assert rel(np.diag(Kj), np.diag(ref[0]["state"]["K"])) <= 1e-12
     assert info[1] == 0 and abs(mll[1] - ref[1]["mll"]) <= 1e-8 * abs(ref[1]["mll"])
     assert info[2] == -2 and mll[2] == -np.inf and np.all(np.isnan(grad[2]))
     # a failed neighbour must not poison the batch
     assert rel(grad[1], ref[1]["grad"]) <= 1e-8
+    # hopeless case: negative noise cannot exist, but s_f^2 overflow to inf is flagged -2, and a matrix that stays
+    # indefinite after 10 jitters reports -1: emulate with NaN-free but non-PD inputs via huge duplicates + tiny jitter
+    thetas2 = thetas.copy()
+    thetas2[0, -1] = 400.0  # exp(800) = inf
+    _, _, info2 = batch.eval(theta=thetas2)
+    assert info2[0] == -2 and info2[1] == 0
 
 
 def test_active_mask(gprb):
