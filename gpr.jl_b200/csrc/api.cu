@@ -36,7 +36,7 @@ static int dev_alloc(T** p, size_t count) {
 static void free_batch(gprb_batch* b) {
   if (!b) return;
   cudaFree(b->Xptr); cudaFree(b->Xtptr); cudaFree(b->ymm); cudaFree(b->theta); cudaFree(b->A); cudaFree(b->Lm);
-  cudaFree(b->Dinv); cudaFree(b->DinvT); cudaFree(b->alpha); cudaFree(b->zbuf); cudaFree(b->jitter);
+  cudaFree(b->Dinv); cudaFree(b->DinvT); cudaFree(b->KinvD); cudaFree(b->alpha); cudaFree(b->zbuf); cudaFree(b->jitter);
   cudaFree(b->logdet_part); cudaFree(b->fail); cudaFree(b->mll); cudaFree(b->grad);
   cudaFree(b->grad_part); cudaFree(b->list);
   if (b->list_host) cudaFreeHost(b->list_host);
@@ -78,8 +78,9 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
   if ((rc = launch_assemble(aa, count, st))) return rc;
   ++launches;
   if (prof) cudaEventRecord(b->ev[1], st);
-  GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG};
-  DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0};
+  const int nv = (int)((b->n + KT - 1) / KT * KT);
+  GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, b->KinvD, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG, nv};
+  DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
   for (int j = 0; j < J; ++j) {
     ga.step = j; ga.mode = GEMM_CHOL_DIAG;
     if ((rc = gemm(ga, 1))) return rc;
@@ -94,7 +95,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
   }
   if (prof) cudaEventRecord(b->ev[2], st);
   SolveArgs sa{b->Lm, b->Dinv, b->ymm, b->logdet_part, b->fail, b->zbuf, b->alpha, b->mll, list, ms, dstride,
-               (int)b->n, (int)b->npad, J};
+               (int)b->n, (int)b->npad, J, nv};
   if ((rc = launch_solve(sa, count, st))) return rc;
   ++launches;
   if (prof) cudaEventRecord(b->ev[3], st);
@@ -109,7 +110,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
     if ((rc = gemm(ga, J * (J + 1) / 2))) return rc;
     ++launches;
     if (prof) cudaEventRecord(b->ev[4], st);
-    GradArgs gr{b->Xtptr, b->theta, b->A, b->alpha, b->grad_part, b->grad, b->fail, list, ms,
+    GradArgs gr{b->Xtptr, b->theta, b->A, b->KinvD, b->alpha, b->grad_part, b->grad, b->fail, list, ms, dstride,
                 (int)b->n, (int)b->npad, b->d, J, b->kind};
     if ((rc = launch_grad(gr, count, st))) return rc;
     launches += 2;
@@ -337,7 +338,7 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
   do {
     if ((rc = dev_alloc(&b->Xptr, B)) || (rc = dev_alloc(&b->Xtptr, B)) || (rc = dev_alloc(&b->ymm, (size_t)B * b->npad)) ||
         (rc = dev_alloc(&b->theta, (size_t)B * b->P)) || (rc = dev_alloc(&b->A, mat * B)) || (rc = dev_alloc(&b->Lm, mat * B)) ||
-        (rc = dev_alloc(&b->Dinv, dinv * B)) || (rc = dev_alloc(&b->DinvT, dinv * B)) ||
+        (rc = dev_alloc(&b->Dinv, dinv * B)) || (rc = dev_alloc(&b->DinvT, dinv * B)) || (rc = dev_alloc(&b->KinvD, dinv * B)) ||
         (rc = dev_alloc(&b->alpha, (size_t)B * b->npad)) || (rc = dev_alloc(&b->zbuf, (size_t)B * b->npad)) ||
         (rc = dev_alloc(&b->jitter, B)) || (rc = dev_alloc(&b->logdet_part, (size_t)B * b->J)) ||
         (rc = dev_alloc(&b->fail, B)) || (rc = dev_alloc(&b->mll, B)) || (rc = dev_alloc(&b->grad, (size_t)B * b->P)) ||
@@ -484,8 +485,8 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
     int rc = upload_list(b, ninv);
     if (rc) return rc;
     const int J = b->J;
-    GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->list, b->npad * b->npad, (int64_t)J * NB * NB,
-                (int)b->npad, J, 0, GEMM_TRTRI_ROW};
+    GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->KinvD, b->list, b->npad * b->npad, (int64_t)J * NB * NB,
+                (int)b->npad, J, 0, GEMM_TRTRI_ROW, (int)((b->n + KT - 1) / KT * KT)};
     for (int i = 1; i < J; ++i) {
       ga.step = i;
       if ((rc = launch_tile_gemm(ga, i, ninv, st))) return rc;
@@ -527,25 +528,9 @@ static int fetch_matrix(gprb_batch* b, const double* dev, std::vector<double>& h
 int gprb_get_K(gprb_batch* b, int32_t gp, double* out) {
   GPRB_REQUIRE(b && out && gp >= 0 && gp < b->B, "gprb_get_K: bad argument");
   GPRB_REQUIRE(b->state_ok[gp], "gprb_get_K: no evaluated state");
-  GPRB_CUDA(cudaSetDevice(b->ctx->device));
-  // K is overwritten by K^-1 after a gradient evaluation: re-assemble it (theta and jitter are resident)
-  double* scratch = nullptr;
-  int32_t* fl = nullptr;
-  int rc;
-  if ((rc = dev_alloc(&scratch, (size_t)b->npad * b->npad))) return rc;
-  if ((rc = dev_alloc(&fl, b->B))) { cudaFree(scratch); return rc; }
-  b->list_host[0] = gp;
-  rc = upload_list(b, 1);
-  if (!rc) {
-    // assemble GP `gp` into scratch: shift the base pointer so that gp * mat_stride lands on scratch
-    const int64_t ms = b->npad * b->npad;
-    AssembleArgs aa{b->Xtptr, b->theta, b->jitter, scratch - (int64_t)gp * ms, fl, b->list, ms, (int)b->n, (int)b->npad,
-                    b->d, b->J, b->kind};
-    rc = launch_assemble(aa, 1, b->stream[0]);
-  }
+  // K (noise and make_posdef! jitter included) stays resident in the lower tiles of A through every stage
   std::vector<double> h;
-  if (!rc) rc = fetch_matrix(b, scratch, h);
-  cudaFree(scratch); cudaFree(fl);
+  int rc = fetch_matrix(b, b->A + (size_t)gp * b->npad * b->npad, h);
   if (rc) return rc;
   const int64_t n = b->n, np = b->npad;
   for (int64_t c = 0; c < n; ++c)
@@ -580,9 +565,17 @@ int gprb_get_Kinv(gprb_batch* b, int32_t gp, double* out) {
   std::vector<double> h;
   int rc = fetch_matrix(b, b->A + (size_t)gp * b->npad * b->npad, h);
   if (rc) return rc;
+  const size_t dn = (size_t)b->J * NB * NB;
+  std::vector<double> dg(dn);
+  GPRB_CUDA(cudaMemcpy(dg.data(), b->KinvD + (size_t)gp * dn, sizeof(double) * dn, cudaMemcpyDeviceToHost));
   const int64_t n = b->n, np = b->npad;
   for (int64_t c = 0; c < n; ++c)
-    for (int64_t r = 0; r < n; ++r) out[r + c * n] = h[r + c * np];
+    for (int64_t r = c; r < n; ++r) {
+      const int64_t ti = r / NB, tj = c / NB, rl = r % NB, cl = c % NB;
+      // tile (ti,tj), ti > tj, lives un-transposed at tile position (tj,ti); diagonal tiles in KinvD
+      const double v = (ti == tj) ? dg[(size_t)ti * NB * NB + rl + cl * NB] : h[(tj * NB + rl) + (ti * NB + cl) * np];
+      out[r + c * n] = out[c + r * n] = v;
+    }
   return GPRB_OK;
 }
 

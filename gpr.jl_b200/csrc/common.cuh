@@ -53,7 +53,8 @@ struct gprb_dataset {
 };
 
 // Per-GP device state (structure-of-arrays over the batch), all resident in HBM:
-//   A   [B][npad*npad]  K (lower tiles) after assembly; K^-1 (lower tiles) after the inverse stage
+//   A   [B][npad*npad]  K in the lower tiles (kept); after the inverse stage the strictly-upper tile (j,i) holds the
+//                       K^-1 tile (i,j) un-transposed, and KinvD the diagonal tiles of K^-1
 //   Lm  [B][npad*npad]  L (lower tiles, K = L L^T) and V = L^-T (strictly-upper tiles)
 //   Dinv/DinvT [B][J][NB*NB]  inverse of each diagonal block of L, and its transpose
 struct gprb_batch {
@@ -71,6 +72,7 @@ struct gprb_batch {
   double* Lm = nullptr;
   double* Dinv = nullptr;
   double* DinvT = nullptr;
+  double* KinvD = nullptr;        // [B][J][NB*NB] diagonal tiles of K^-1
   double* alpha = nullptr;        // [B][npad]
   double* zbuf = nullptr;         // [B][npad] forward-substitution result
   double* jitter = nullptr;       // [B] cumulative diagonal jitter added this evaluation

@@ -159,8 +159,15 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_grad_tiles(GradArgs g) {
   const double sf2 = exp(2.0 * th[d + 1]);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   double m[8][8];
-  pair_r2(Xi, Xj, w, d, tx, ty, m);  // m holds r2 for now
-  const double* Kinv = g.Kinv + (int64_t)gp * g.mat_stride;
+  // SEArd: dK/dll_p = K_f w_p Delta_p^2 and K_f,ij (i != j) is still resident in the lower tiles of A, so the
+  // distance pass and the exp are skipped; the Matern kernels need r itself and recompute it.
+  constexpr bool REUSE_K = (KIND == GPRB_KERNEL_SE_ARD);
+  if (!REUSE_K) pair_r2(Xi, Xj, w, d, tx, ty, m);  // m holds r2 for now
+  const double* Kt = g.A + (int64_t)gp * g.mat_stride + (int64_t)ti * NB + (int64_t)tj * NB * g.npad;  // K tile (ti,tj)
+  const double* Kinv;
+  int64_t ldk;
+  if (ti == tj) { Kinv = g.KinvD + (int64_t)gp * g.dinv_stride + (int64_t)ti * NB * NB; ldk = NB; }
+  else { Kinv = g.A + (int64_t)gp * g.mat_stride + (int64_t)tj * NB + (int64_t)ti * NB * g.npad; ldk = g.npad; }
   const double* alpha = g.alpha + (int64_t)gp * g.npad;
   const int n = g.n;
   double s_sig = 0.0, s_tr = 0.0;
@@ -169,20 +176,26 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_grad_tiles(GradArgs g) {
   for (int a = 0; a < 8; ++a) ar[a] = alpha[ti * NB + loc8(a, tx)];
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
-    const int c = tj * NB + loc8(b, ty);
+    const int cl = loc8(b, ty), c = tj * NB + cl;
     const double ac = alpha[c];
 #pragma unroll
     for (int a = 0; a < 8; a += 2) {
-      const int r = ti * NB + loc8(a, tx);
-      const double2 kv = *reinterpret_cast<const double2*>(Kinv + r + (int64_t)c * g.npad);
+      const int rl = loc8(a, tx), r = ti * NB + rl;
+      const double2 kv = *reinterpret_cast<const double2*>(Kinv + rl + (int64_t)cl * ldk);
       const double kin[2] = {kv.x, kv.y};
+      double kst[2] = {0.0, 0.0};
+      if (REUSE_K) {
+        const double2 ks = *reinterpret_cast<const double2*>(Kt + rl + (int64_t)cl * g.npad);
+        kst[0] = ks.x; kst[1] = ks.y;
+      }
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        double kf, gf;
-        kfun<KIND>(m[a + e][b], sf2, kf, gf);
         const int rr = r + e;
+        double kf, gf;
+        if (REUSE_K) { kf = (rr == c) ? sf2 : kst[e]; gf = kf; }
+        else kfun<KIND>(m[a + e][b], sf2, kf, gf);
         double q = ar[a + e] * ac - kin[e];
-        if (rr >= n || c >= n) q = 0.0;
+        if (rr >= n || c >= n) { q = 0.0; kf = 0.0; gf = 0.0; }
         s_sig = fma(q, kf, s_sig);
         if (rr == c) s_tr += q;
         m[a + e][b] = q * gf;

@@ -8,110 +8,194 @@
 namespace gprb {
 
 constexpr int DIAG_THREADS = 256;
-constexpr int LDD = NB + 1;  // padded column stride of the smem block
+constexpr int SB = 32;            // sub-block edge inside the 128x128 diagonal block
+constexpr int NSB = NB / SB;      // 4
+constexpr int LDW = SB + 4;       // padded column stride of the 32x32 side buffers (conflict-free DMMA fragments)
+constexpr unsigned FULL = 0xffffffffu;
 
-// One CTA per GP: Lm(j,j) holds S = K(j,j) - sum_k L(j,k) L(j,k)^T on entry (lower part valid).
-// On exit: Lm(j,j) = L_jj (zeros above the diagonal), Dinv[j] = inv(L_jj), DinvT[j] = its transpose,
-// logdet_part[j] = sum log diag(L_jj), fail = LAPACK-style info (first non-positive / NaN pivot, 1-based).
+// acc(8 x 32 slab) += A(8 x 4*ksteps) * B(32 x 4*ksteps)^T on the DMMA pipe, operands "k-major" in smem:
+// A(m,k) = Abase[k*lda + m], B(n,k) = Bbase[k*ldb + n];  lane = 4g+t owns acc[ni] = C(g, ni*8 + 2t + {0,1}).
+__device__ __forceinline__ void slab_mma(double (&acc)[4][2], const double* Abase, int lda, const double* Bbase, int ldb,
+                                         int ksteps, int g, int t) {
+  for (int k4 = 0; k4 < ksteps; ++k4) {
+    const double a = Abase[(k4 * 4 + t) * lda + g];
+    const double* bp = Bbase + (k4 * 4 + t) * ldb + g;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) dmma884(acc[ni][0], acc[ni][1], a, bp[ni * 8]);
+  }
+}
+
+// One CTA per GP.  On entry Lm(j,j) holds S = K(j,j) - sum_k L(j,k) L(j,k)^T (lower part valid).
+// On exit: Lm(j,j) = L_jj, Dinv[j] = inv(L_jj), DinvT[j] = inv(L_jj)^T, logdet_part[j] = sum log diag(L_jj),
+// fail = LAPACK-style info (first non-positive / NaN pivot, 1-based) when the block is not positive definite.
+//
+// Blocked inside shared memory with 32x32 sub-blocks: the sub-block on the diagonal is factorised and inverted by
+// ONE warp entirely in registers (row per lane, pivots broadcast by shuffles); panel solves, trailing updates and
+// the blocked triangular inverse are 8x32 DMMA slabs spread over the 8 warps.  S (col-major, ld 132) ends up as
+// [ L off-diagonal sub-blocks (lower) | W^T = inv(L)^T (upper, diagonal sub-blocks included) ].
 __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* S = reinterpret_cast<double*>(smem_raw);  // S(r,c) = S[r + c*LDD]
-  double* diagW = S + NB * LDD;                      // 1 / L(c,c)
+  double* S = reinterpret_cast<double*>(smem_raw);   // S(r,c) = S[c*LDS_T + r]
+  double* Dd = S + NB * LDS_T;                        // [NSB][SB*LDW]  W_dd col-major: Dd[r + c*LDW]
+  double* Tb = Dd + NSB * SB * LDW;                   // [NSB-1][SB*LDW] scratch T(k,n) = Tb[k*LDW + n]
   __shared__ int bad_col;
+  __shared__ double dinv32[SB];
   const int gp = g.list ? g.list[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
   const int j = g.step;
   const int64_t npad = g.npad;
   if (g.fail[gp] != 0) return;  // already failed (or non-finite theta): results are discarded by the host
   double* T = g.Lm + (int64_t)gp * g.mat_stride + (int64_t)j * NB + (int64_t)j * NB * npad;
+  // rows / cols beyond nv are padding the GEMM stages neither compute nor read: treat them as the identity here
+  const int nvl = (j == g.J - 1) ? g.nv - j * NB : NB;
   for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
     const int r = idx & (NB - 1), c = idx >> 7;
-    S[r + c * LDD] = T[r + c * npad];
+    S[c * LDS_T + r] = (r < nvl && c < nvl) ? T[r + c * npad] : (r == c ? 1.0 : 0.0);
   }
   if (tid == 0) bad_col = 0;
-
-  // ---- unblocked right-looking Cholesky (lower), LAPACK dpotf2 failure rule: pivot <= 0 or NaN
-  for (int c = 0; c < NB; ++c) {
-    __syncthreads();
-    double piv = S[c + c * LDD];
-    if (!(piv > 0.0)) {
-      if (tid == 0 && bad_col == 0) bad_col = c + 1;
-      piv = 1.0;
-    }
-    const double l = sqrt(piv);
-    const double inv = 1.0 / l;
-    __syncthreads();
-    for (int r = c + 1 + tid; r < NB; r += DIAG_THREADS) S[r + c * LDD] *= inv;
-    if (tid == 0) S[c + c * LDD] = l;
-    __syncthreads();
-    for (int k = c + 1 + warp; k < NB; k += DIAG_THREADS / 32) {
-      const double lk = S[k + c * LDD];
-      for (int r = k + lane; r < NB; r += 32) S[r + k * LDD] = fma(-S[r + c * LDD], lk, S[r + k * LDD]);
-    }
-  }
   __syncthreads();
+  double logdet = 0.0;
+
+  // ================= phase A: right-looking Cholesky over 32-wide sub-block columns =================
+  for (int jj = 0; jj < NSB; ++jj) {
+    const int j0 = jj * SB;
+    if (warp == 0) {
+      // ---- A1: potf2 + trtri of the 32x32 diagonal sub-block by one warp, lane r owns row r / column r.
+      // Rolled loops over shared memory (a fully unrolled register version is instruction-fetch bound).
+      double* D = S + j0 * LDS_T + j0;  // D(r,c) = D[c*LDS_T + r]
+      int bad = 0;
+      // left-looking (dot-product) form: only loads + FMAs inside the k loop, one store per column
+      for (int c = 0; c < SB; ++c) {
+        double a0 = 0.0, a1 = 0.0;
+        int k = 0;
+        for (; k + 1 < c; k += 2) {
+          a0 = fma(D[k * LDS_T + lane], D[k * LDS_T + c], a0);              // L(lane,k) L(c,k)
+          a1 = fma(D[(k + 1) * LDS_T + lane], D[(k + 1) * LDS_T + c], a1);
+        }
+        if (k < c) a0 = fma(D[k * LDS_T + lane], D[k * LDS_T + c], a0);
+        const double v = D[c * LDS_T + lane] - (a0 + a1);                    // valid for lane >= c
+        double piv = __shfl_sync(FULL, v, c);
+        if (!(piv > 0.0)) {  // LAPACK dpotf2 rule: pivot <= 0 or NaN
+          if (bad == 0) bad = j0 + c + 1;
+          piv = 1.0;
+        }
+        const double l = sqrt(piv);
+        const double inv = 1.0 / l;
+        logdet += log(l);
+        if (lane > c) D[c * LDS_T + lane] = v * inv;
+        else if (lane == c) { D[c * LDS_T + c] = l; dinv32[c] = inv; }
+        __syncwarp();
+      }
+      if (bad != 0 && lane == 0 && bad_col == 0) bad_col = bad;
+      // L_dd straight to HBM (lower), zeros above the diagonal
+      for (int c = 0; c < SB; ++c) T[(j0 + lane) + (int64_t)(j0 + c) * npad] = (lane >= c) ? D[c * LDS_T + lane] : 0.0;
+      // W = inv(L_dd): lane c owns column c; W(r,c), r > c, is parked transposed at D(c,r) (strict upper part)
+      const double wcc = dinv32[lane];
+      for (int r = 1; r < SB; ++r) {
+        double s0 = 0.0, s1 = 0.0;
+        if (r > lane) {
+          s0 = D[lane * LDS_T + r] * wcc;  // L(r,c) W(c,c)
+          int k = lane + 1;
+          for (; k + 1 < r; k += 2) {
+            s0 = fma(D[k * LDS_T + r], D[k * LDS_T + lane], s0);
+            s1 = fma(D[(k + 1) * LDS_T + r], D[(k + 1) * LDS_T + lane], s1);
+          }
+          if (k < r) s0 = fma(D[k * LDS_T + r], D[k * LDS_T + lane], s0);
+          D[r * LDS_T + lane] = -(s0 + s1) * dinv32[r];
+        }
+        __syncwarp();
+      }
+      // finalise: D becomes W_dd^T (upper incl. diagonal, zeros below); Dd[jj] gets W_dd column-major
+      double* Dj = Dd + jj * SB * LDW;
+      for (int r = 0; r < SB; ++r) {
+        double wt;  // W^T(lane, r) = W(r, lane)
+        if (r > lane) wt = D[r * LDS_T + lane];
+        else if (r == lane) wt = wcc;
+        else wt = 0.0;
+        __syncwarp();
+        D[r * LDS_T + lane] = wt;
+        Dj[r + lane * LDW] = wt;  // W(r, lane)
+      }
+    }
+    __syncthreads();
+    // ---- A2: panel  L(i, jj) = S(i, jj) * W_dd^T  for the rows below the sub-block; 8-row slabs over the warps
+    const int nslab_panel = (NB - j0 - SB) / 8;
+    for (int sl = warp; sl < nslab_panel; sl += DIAG_THREADS / 32) {
+      const int rbase = j0 + SB + sl * 8;
+      double acc[4][2] = {};
+      slab_mma(acc, S + j0 * LDS_T + rbase, LDS_T, Dd + jj * SB * LDW, LDW, SB / 4, gq, t);
+      __syncwarp();
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        S[(j0 + ni * 8 + 2 * t) * LDS_T + rbase + gq] = acc[ni][0];
+        S[(j0 + ni * 8 + 2 * t + 1) * LDS_T + rbase + gq] = acc[ni][1];
+      }
+    }
+    __syncthreads();
+    // ---- A3: trailing update  S(bi, bk) -= L(bi, jj) L(bk, jj)^T  for jj < bk <= bi
+    const int nrem = NSB - 1 - jj;
+    const int nitems = nrem * (nrem + 1) / 2 * (SB / 8);
+    for (int it = warp; it < nitems; it += DIAG_THREADS / 32) {
+      const int sl = it & 3, blk = it >> 2;
+      int bi = 0;
+      while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+      const int bk = blk - bi * (bi + 1) / 2;
+      const int r0 = (jj + 1 + bi) * SB + sl * 8, c0 = (jj + 1 + bk) * SB;
+      double acc[4][2] = {};
+      slab_mma(acc, S + j0 * LDS_T + r0, LDS_T, S + j0 * LDS_T + c0, LDS_T, SB / 4, gq, t);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        S[(c0 + ni * 8 + 2 * t) * LDS_T + r0 + gq] -= acc[ni][0];
+        S[(c0 + ni * 8 + 2 * t + 1) * LDS_T + r0 + gq] -= acc[ni][1];
+      }
+    }
+    __syncthreads();
+  }
   if (bad_col != 0) {
     if (tid == 0) g.fail[gp] = j * NB + bad_col;
     return;
   }
 
-  // ---- W = inv(L): two threads per column c (k-parity split), W(r,c) r>c parked at S(c,r) (strict upper)
-  {
-    const int c = tid >> 1, half = tid & 1;
-    const double wcc = 1.0 / S[c + c * LDD];
-    if (half == 0) diagW[c] = wcc;
-    // warp-uniform row loop (lanes of a warp own columns 16*warp .. 16*warp+15), predicated on r > c
-    for (int r = 16 * warp + 1; r < NB; ++r) {
-      // s = sum_{k=c}^{r-1} L(r,k) W(k,c)
-      double s0 = 0.0, s1 = 0.0;
-      if (r > c) {
-        int k = c + half;
-        if (half == 0) { s0 = S[r + c * LDD] * wcc; k += 2; }
-        for (; k + 2 < r; k += 4) {
-          s0 = fma(S[r + k * LDD], S[c + k * LDD], s0);
-          s1 = fma(S[r + (k + 2) * LDD], S[c + (k + 2) * LDD], s1);
-        }
-        for (; k < r; k += 2) s0 = fma(S[r + k * LDD], S[c + k * LDD], s0);
-      }
-      double s = s0 + s1;
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      if (r > c && half == 0) S[c + r * LDD] = -s / S[r + r * LDD];
-      __syncwarp();
+  // ================= phase B: blocked inverse, W(i,j) = -W_ii * sum_{k=j}^{i-1} L(i,k) W(k,j), kept as W^T =========
+  for (int i = 1; i < NSB; ++i) {
+    const int i0 = i * SB;
+    // B1: T_j (32x32) = L(i, j..i-1) * W(j..i-1, j)   -- one contiguous k-range thanks to the W^T layout of S
+    for (int it = warp; it < i * (SB / 8); it += DIAG_THREADS / 32) {
+      const int sl = it & 3, jb = it >> 2, j0 = jb * SB;
+      double acc[4][2] = {};
+      slab_mma(acc, S + j0 * LDS_T + i0 + sl * 8, LDS_T, S + j0 * LDS_T + j0, LDS_T, (i - jb) * (SB / 4), gq, t);
+      double* Tj = Tb + jb * SB * LDW;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+        *reinterpret_cast<double2*>(&Tj[(sl * 8 + gq) * LDW + ni * 8 + 2 * t]) = make_double2(acc[ni][0], acc[ni][1]);
     }
+    __syncthreads();
+    // B2: W(i,j) = -W_ii * T_j, stored transposed into the upper sub-block (j,i) of S
+    for (int it = warp; it < i * (SB / 8); it += DIAG_THREADS / 32) {
+      const int sl = it & 3, jb = it >> 2, j0 = jb * SB;
+      double acc[4][2] = {};
+      slab_mma(acc, Dd + i * SB * LDW + sl * 8, LDW, Tb + jb * SB * LDW, LDW, SB / 4, gq, t);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+        *reinterpret_cast<double2*>(&S[(i0 + sl * 8 + gq) * LDS_T + j0 + ni * 8 + 2 * t]) = make_double2(-acc[ni][0], -acc[ni][1]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
+  // ================= write-out =================
   double* Dinv = g.Dinv + (int64_t)gp * g.dinv_stride + (int64_t)j * NB * NB;
   double* DinvT = g.DinvT + (int64_t)gp * g.dinv_stride + (int64_t)j * NB * NB;
   for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
     const int r = idx & (NB - 1), c = idx >> 7;
-    const double lrc = S[r + c * LDD];           // L(r,c) if r >= c, W(c,r)... careful below
-    // element (r,c): lower part of S holds L, strict upper part holds W transposed (S(c',r') = W(r',c'))
-    double Lval, Wval, WTval;
-    if (r > c) {
-      Lval = lrc;                 // L(r,c)
-      Wval = S[c + r * LDD];      // W(r,c) parked at S(c,r)
-      WTval = 0.0;                // W^T(r,c) = W(c,r) = 0 (c < r)
-    } else if (r == c) {
-      Lval = lrc;
-      Wval = diagW[c];
-      WTval = diagW[c];
-    } else {
-      Lval = 0.0;
-      Wval = 0.0;
-      WTval = lrc;                // W^T(r,c) = W(c,r), c > r, parked at S(r,c)
-    }
-    T[r + c * npad] = Lval;
-    Dinv[idx] = Wval;
-    DinvT[idx] = WTval;
+    const int br = r / SB, bc = c / SB;
+    // S(r,c): lower off-diagonal sub-blocks = L ; upper incl. diagonal sub-blocks = W^T
+    if (br > bc) T[r + c * npad] = S[c * LDS_T + r];
+    else if (br < bc) T[r + c * npad] = 0.0;
+    DinvT[idx] = (br <= bc) ? S[c * LDS_T + r] : 0.0;   // W^T(r,c)
+    Dinv[idx] = (br >= bc) ? S[r * LDS_T + c] : 0.0;    // W(r,c) = W^T(c,r)
   }
-  if (warp == 0) {
-    double s = 0.0;
-    for (int r = lane; r < NB; r += 32) s += log(S[r + r * LDD]);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) g.logdet_part[(int64_t)gp * g.J + j] = s;
-  }
+  if (tid == 0) g.logdet_part[(int64_t)gp * g.J + j] = logdet;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -139,10 +223,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
   const int row = tid & (NB - 1), part = tid >> 7;  // 4 k-partitions
 
   // ---- forward: z_j = Dinv_j (y_j - sum_{k<j} L(j,k) z_k)
+  const int nv = g.nv;
   for (int jb = 0; jb < J; ++jb) {
     const double* Lrow = L + (int64_t)jb * NB + row;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    const int kend = jb * NB;
+    const int kend = (jb * NB + row < nv) ? jb * NB : 0;  // padding rows: z = 0
     int k = part;
     for (; k + 12 < kend; k += 16) {
       a0 = fma(Lrow[(int64_t)k * npad], z[k], a0);
@@ -171,11 +256,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
       const double* Lcol = L + (int64_t)(jb * NB + c) * npad;
       double a0 = 0.0, a1 = 0.0;
       int r = rbeg + lane;
-      for (; r + 32 < (int)npad; r += 64) {
+      for (; r + 32 < nv; r += 64) {
         a0 = fma(Lcol[r], al[r], a0);
         a1 = fma(Lcol[r + 32], al[r + 32], a1);
       }
-      for (; r < (int)npad; r += 32) a0 = fma(Lcol[r], al[r], a0);
+      for (; r < nv; r += 32) a0 = fma(Lcol[r], al[r], a0);
       double s = a0 + a1;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -213,7 +298,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
 
 int launch_diag_factor(const DiagArgs& a, int count, cudaStream_t stream) {
   if (count <= 0) return 0;
-  const size_t smem = (size_t)(NB * LDD + NB) * sizeof(double);
+  const size_t smem = (size_t)(NB * LDS_T + NSB * SB * LDW + (NSB - 1) * SB * LDW) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_diag_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

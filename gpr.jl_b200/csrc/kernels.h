@@ -13,9 +13,11 @@ struct GemmArgs {
   const double* Dinv;   // inverse diagonal blocks (post-multiplier)
   const double* Cin;    // K tiles for the Cholesky modes
   double* Cout;
+  double* KinvD;        // [B][J][NB*NB] diagonal tiles of K^-1 (LAUUM output)
   const int32_t* list;  // GP index per blockIdx.y (nullptr = identity)
   int64_t mat_stride, dinv_stride;
   int npad, J, step, mode;
+  int nv;               // n rounded up to 16: rows / k beyond it are padding that is neither computed nor read
 };
 
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream);
@@ -43,6 +45,7 @@ struct DiagArgs {
   const int32_t* list;
   int64_t mat_stride, dinv_stride;
   int npad, J, step;
+  int nv;
 };
 int launch_diag_factor(const DiagArgs& a, int count, cudaStream_t stream);
 
@@ -59,6 +62,7 @@ struct SolveArgs {
   const int32_t* list;
   int64_t mat_stride, dinv_stride;
   int n, npad, J;
+  int nv;
 };
 int launch_solve(const SolveArgs& a, int count, cudaStream_t stream);
 
@@ -66,13 +70,14 @@ int launch_solve(const SolveArgs& a, int count, cudaStream_t stream);
 struct GradArgs {
   const double* const* Xt;
   const double* theta;
-  const double* Kinv;   // A buffer, full symmetric K^-1
+  const double* A;      // lower tiles: K (intact); strictly-upper tile (j,i): K^-1 tile (i,j), un-transposed
+  const double* KinvD;  // [B][J][NB*NB] diagonal tiles of K^-1
   const double* alpha;
   double* part;         // [B][ntiles][P + 1]
   double* grad;         // [B][P]
   const int32_t* fail;
   const int32_t* list;
-  int64_t mat_stride;
+  int64_t mat_stride, dinv_stride;
   int n, npad, d, J, kind;
 };
 int launch_grad(const GradArgs& a, int count, cudaStream_t stream);

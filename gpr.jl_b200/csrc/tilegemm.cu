@@ -12,7 +12,7 @@
 //   CHOL_DIAG  S(j,j)   = K(j,j) - sum_{k<j} L(j,k) L(j,k)^T                      -> Lm(j,j)   (potf2 follows)
 //   CHOL_COL   L(i,j)   = [K(i,j) - sum_{k<j} L(i,k) L(j,k)^T] * inv(L_jj)^T      -> Lm(i,j)   i > j = step
 //   TRTRI_ROW  W(i,j)   = -inv(L_ii) * sum_{k=j}^{i-1} L(i,k) W(k,j)   stored as V(j,i) = W(i,j)^T, i = step
-//   LAUUM      Kinv(i,j) = sum_{k>=i} V(i,k) V(j,k)^T  (i >= j), mirrored to (j,i) -> A
+//   LAUUM      Kinv(i,j) = sum_{k>=i} V(i,k) V(j,k)^T  (i >= j)  -> upper tile (j,i) of A (un-transposed) / KinvD(i)
 // where V = L^-T lives in the strictly-upper tiles of Lm and its diagonal blocks in DinvT.
 #include "common.cuh"
 #include "kernels.h"
@@ -59,74 +59,20 @@ __device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int b
   return tc;
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* stages = reinterpret_cast<double*>(smem_raw);
-  double* rbuf = stages + NSTAGE * STAGE_DOUBLES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + 2 * RBUF_DOUBLES);
-  uint64_t* full = bars;            // [NSTAGE]
-  uint64_t* empty = bars + NSTAGE;  // [NSTAGE]
-  uint64_t* rfull = bars + 2 * NSTAGE;      // [2]
-  uint64_t* rempty = bars + 2 * NSTAGE + 2; // [2]
-
+// Consumer side of one tile (warps 0-7).  RAGGED = the tile touches the padded tail of the last block row:
+// only then are the DMMAs / loads / stores predicated per 8-row slab (mi < mi_valid); full tiles run the clean loop.
+template <bool RAGGED>
+__device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord& tc, double* stages, double* rbuf,
+                                             uint64_t* full, uint64_t* empty, uint64_t* rfull, uint64_t* rempty,
+                                             int gp, int nchunks, int rows_valid) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
-  const TileCoord tc = tile_coord(g.mode, g.step, g.J, blockIdx.x);
   const int64_t npad = g.npad;
-  const double* Lm = g.Lm + (int64_t)gp * g.mat_stride;
-  const double* DinvT = g.DinvT + (int64_t)gp * g.dinv_stride;
-  const double* Dinv = g.Dinv + (int64_t)gp * g.dinv_stride;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], N_CONSUMER_WARPS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], N_CONSUMER_WARPS); }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  const int nchunks = (tc.kb1 - tc.kb0) * (NB / KT);
-
-  if (warp == N_CONSUMER_WARPS) {
-    // ===================== producer warp =====================
-    int stage = 0; uint32_t phase = 0;
-    int rissued = 0;
-    auto issue_r = [&](int c) {  // chunk c of the post-multiplier -> rbuf[c & 1]
-      const int buf = c & 1;
-      mbar_wait(&rempty[buf], ((c >> 1) & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(&rfull[buf], KT * NB * sizeof(double));
-      __syncwarp();
-      if (lane < KT) {
-        const double* src = Dinv + (int64_t)tc.rblk * NB * NB + (int64_t)(c * KT + lane) * NB;
-        bulk_g2s(rbuf + buf * RBUF_DOUBLES + lane * LDS_T, src, NB * sizeof(double), &rfull[buf]);
-      }
-    };
-    if (tc.post) { issue_r(0); issue_r(1); rissued = 2; }
-    for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-      const double* srcA; const double* srcB; int64_t ldA, ldB;
-      if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }
-      else { srcA = Lm + (int64_t)tc.i * NB + (int64_t)kb * NB * npad; ldA = npad; }
-      if (kb == tc.b_diag_kb) { srcB = DinvT + (int64_t)kb * NB * NB; ldB = NB; }
-      else { srcB = Lm + (int64_t)tc.j * NB + (int64_t)kb * NB * npad; ldB = npad; }
-      for (int c = 0; c < NB / KT; ++c) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        if (lane == 0) mbar_expect_tx(&full[stage], 2 * KT * NB * sizeof(double));
-        __syncwarp();
-        double* dst = stages + stage * STAGE_DOUBLES;
-        if (lane < KT) bulk_g2s(dst + lane * LDS_T, srcA + (int64_t)(c * KT + lane) * ldA, NB * sizeof(double), &full[stage]);
-        else bulk_g2s(dst + KT * LDS_T + (lane - KT) * LDS_T, srcB + (int64_t)(c * KT + lane - KT) * ldB, NB * sizeof(double), &full[stage]);
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-      }
-    }
-    if (tc.post) for (; rissued < NB / KT; ++rissued) issue_r(rissued);
-    return;
-  }
-
-  // ===================== consumer warps =====================
   // SMSP s = warp & 3 hosts warps {s, s+4}; pair column groups {0,3} / {1,2} on one SMSP so the
   // triangular skips of the post-multiply balance across the four DMMA pipes.
   const int s4 = warp & 3, h = warp >> 2;
-  const int wm = s4 & 1;
-  const int wn = (s4 >> 1) ? (1 + h) : (3 * h);
+  const int wm = h;                    // each SMSP hosts one wm = 0 and one wm = 1 warp (row-padding skip balances)
+  const int wn = h ? (3 - s4) : s4;    // ... with column groups {s, 3-s} (triangular post-multiply skip balances)
+  const int mi_valid = RAGGED ? min(8, max(0, (rows_valid - wm * 64 + 7) / 8)) : 8;
   const int gq = lane >> 2, t = lane & 3;
   const int row0 = wm * 64 + gq;  // + mi*8
   const int col0 = wn * 32 + gq;  // + ni*8  (operand row index of B)
@@ -154,8 +100,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
         for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
+          if (!RAGGED || mi < mi_valid) {
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -171,6 +119,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
+        if (RAGGED && mi >= mi_valid) continue;
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
         acc[mi][ni][0] = Cin[r + (int64_t)cc * npad] - acc[mi][ni][0];
         acc[mi][ni][1] = Cin[r + (int64_t)(cc + 1) * npad] - acc[mi][ni][1];
@@ -179,16 +128,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
 
   double* Cout = g.Cout + (int64_t)gp * g.mat_stride;
   if (tc.post == 0) {
+    // CHOL_DIAG: S(j,j) -> Lm(j,j).  LAUUM: K^-1(i,j), i > j, goes un-transposed into the free upper tile (j,i) of A
+    // (K stays intact in the lower tiles for the gradient stage); diagonal tiles go to the KinvD side buffer.
+    double* out = Cout + grow + gcol * npad;
+    int64_t ldo = npad;
+    if (g.mode == GEMM_LAUUM) {
+      if (tc.i != tc.j) out = Cout + gcol + grow * npad;
+      else { out = g.KinvD + (int64_t)gp * g.dinv_stride + (int64_t)tc.i * NB * NB; ldo = NB; }
+    }
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
+        if (RAGGED && mi >= mi_valid) continue;
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        Cout[grow + r + (gcol + cc) * npad] = acc[mi][ni][0];
-        Cout[grow + r + (gcol + cc + 1) * npad] = acc[mi][ni][1];
-        if (g.mode == GEMM_LAUUM && tc.i != tc.j) {  // mirror: full symmetric K^-1 for the gradient / predict stages
-          *reinterpret_cast<double2*>(&Cout[gcol + cc + (grow + r) * npad]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        }
+        out[r + (int64_t)cc * ldo] = acc[mi][ni][0];
+        out[r + (int64_t)(cc + 1) * ldo] = acc[mi][ni][1];
       }
     return;
   }
@@ -202,8 +157,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        Ts[cc * LDS_T + r] = acc[mi][ni][0];
-        Ts[(cc + 1) * LDS_T + r] = acc[mi][ni][1];
+        const bool ok = !RAGGED || mi < mi_valid;  // skipped rows are parked as zeros (finite operands for the second pass)
+        Ts[cc * LDS_T + r] = ok ? acc[mi][ni][0] : 0.0;
+        Ts[(cc + 1) * LDS_T + r] = ok ? acc[mi][ni][1] : 0.0;
       }
   } else {  // B operand: Ts[k][n] = T[k][n]
 #pragma unroll
@@ -211,7 +167,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        *reinterpret_cast<double2*>(&Ts[r * LDS_T + cc]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        const bool ok = !RAGGED || mi < mi_valid;
+        *reinterpret_cast<double2*>(&Ts[r * LDS_T + cc]) = ok ? make_double2(acc[mi][ni][0], acc[mi][ni][1]) : make_double2(0.0, 0.0);
       }
   }
 #pragma unroll
@@ -221,7 +178,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
   named_bar_sync(1, N_CONSUMER_WARPS * 32);
 
   // Dinv is lower triangular: R[x][k] == 0 for k > x.  post 1: x = output column, post 2: x = output row.
-  const int kmax = (tc.post == 1) ? (wn * 32 + 31) : (wm * 64 + 63);
+  const int kmax = (tc.post == 1) ? (wn * 32 + 31) : min(wm * 64 + 63, rows_valid - 1);
   for (int c = 0; c < NB / KT; ++c) {
     const int buf = c & 1;
     mbar_wait(&rfull[buf], (c >> 1) & 1);
@@ -238,8 +195,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
         for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
+          if (!RAGGED || mi < mi_valid) {
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          }
       }
     }
     __syncwarp();
@@ -251,6 +210,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
+        if (RAGGED && mi >= mi_valid) continue;
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
         Cout[grow + r + (gcol + cc) * npad] = acc[mi][ni][0];
         Cout[grow + r + (gcol + cc + 1) * npad] = acc[mi][ni][1];
@@ -260,10 +220,82 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
+        if (RAGGED && mi >= mi_valid) continue;
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
         *reinterpret_cast<double2*>(&Cout[gcol + cc + (grow + r) * npad]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
       }
   }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  double* rbuf = stages + NSTAGE * STAGE_DOUBLES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + 2 * RBUF_DOUBLES);
+  uint64_t* full = bars;            // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;  // [NSTAGE]
+  uint64_t* rfull = bars + 2 * NSTAGE;      // [2]
+  uint64_t* rempty = bars + 2 * NSTAGE + 2; // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  const TileCoord tc = tile_coord(g.mode, g.step, g.J, blockIdx.x);
+  const int64_t npad = g.npad;
+  const double* Lm = g.Lm + (int64_t)gp * g.mat_stride;
+  const double* DinvT = g.DinvT + (int64_t)gp * g.dinv_stride;
+  const double* Dinv = g.Dinv + (int64_t)gp * g.dinv_stride;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], N_CONSUMER_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], N_CONSUMER_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // Padding skip: rows/cols >= nv (n rounded up to the 16-wide chunk) are never computed and never read.
+  // Only the last block row / the last k-block are ragged.
+  const int nvl = g.nv - (g.J - 1) * NB;                          // valid rows of the last 128-block (multiple of 16)
+  const int last_kb_chunks = nvl / KT;                             // chunks of k-block J-1 that hold valid k
+  const int nchunks = (tc.kb1 - tc.kb0) * (NB / KT) - ((tc.kb1 == g.J && tc.kb1 > tc.kb0) ? (NB / KT - last_kb_chunks) : 0);
+  const int rows_valid = (tc.i == g.J - 1) ? nvl : NB;            // valid output rows of this tile
+
+  if (warp == N_CONSUMER_WARPS) {
+    // ===================== producer warp =====================
+    int stage = 0; uint32_t phase = 0;
+    int rissued = 0;
+    auto issue_r = [&](int c) {  // chunk c of the post-multiplier -> rbuf[c & 1]
+      const int buf = c & 1;
+      mbar_wait(&rempty[buf], ((c >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&rfull[buf], KT * NB * sizeof(double));
+      __syncwarp();
+      if (lane < KT) {
+        const double* src = Dinv + (int64_t)tc.rblk * NB * NB + (int64_t)(c * KT + lane) * NB;
+        bulk_g2s(rbuf + buf * RBUF_DOUBLES + lane * LDS_T, src, NB * sizeof(double), &rfull[buf]);
+      }
+    };
+    if (tc.post) { issue_r(0); issue_r(1); rissued = 2; }
+    for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+      const double* srcA; const double* srcB; int64_t ldA, ldB;
+      if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }
+      else { srcA = Lm + (int64_t)tc.i * NB + (int64_t)kb * NB * npad; ldA = npad; }
+      if (kb == tc.b_diag_kb) { srcB = DinvT + (int64_t)kb * NB * NB; ldB = NB; }
+      else { srcB = Lm + (int64_t)tc.j * NB + (int64_t)kb * NB * npad; ldB = npad; }
+      const int cend = (kb == g.J - 1) ? last_kb_chunks : NB / KT;
+      for (int c = 0; c < cend; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) mbar_expect_tx(&full[stage], 2 * KT * NB * sizeof(double));
+        __syncwarp();
+        double* dst = stages + stage * STAGE_DOUBLES;
+        if (lane < KT) bulk_g2s(dst + lane * LDS_T, srcA + (int64_t)(c * KT + lane) * ldA, NB * sizeof(double), &full[stage]);
+        else bulk_g2s(dst + KT * LDS_T + (lane - KT) * LDS_T, srcB + (int64_t)(c * KT + lane - KT) * ldB, NB * sizeof(double), &full[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (tc.post) for (; rissued < NB / KT; ++rissued) issue_r(rissued);
+    return;
+  }
+  if (rows_valid == NB) consume_tile<false>(g, tc, stages, rbuf, full, empty, rfull, rempty, gp, nchunks, rows_valid);
+  else consume_tile<true>(g, tc, stages, rbuf, full, empty, rfull, rempty, gp, nchunks, rows_valid);
 }
 
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream) {
