@@ -322,3 +322,37 @@ def test_full_size_properties_n2000(gprb):
     fd = (mp - mm) / (2 * h)
     for b in range(4):
         assert abs(fd[b] - grad[b] @ v) <= 1e-5 * max(1.0, abs(grad[b] @ v))
+
+
+def test_batched_experiment_equals_per_gp_reference_sequence(gprb):
+    """Batched trial body (experiment.fit_trials + predictdynamics) vs the reference's literal per-GP loop
+    (CPnoise.jl:37-52, predictdynamics.jl:11-19) run through the single-GP API."""
+    from gpr_jl_b200 import data, experiment
+    trials = [data.make_trial("CP", 96, seed=70 + t, n_test=3) for t in range(2)]
+    params = np.exp(np.concatenate([[0.0], data.theta0("CP", trials[0]["X"])[1:-1]]))  # [s_f, l_1..l_d]
+    opts = gprb.Options(iterations=6)
+    batch, res = experiment.fit_trials(trials, params, options=opts)
+    idx = np.array([9, 22, 23, 24]) - 1  # CPnoise.jl:28
+
+    def step_fn(t, states, mu):  # stand-in for getvomega + projectv! + updatestate!
+        nxt = states.copy()
+        nxt[idx, :] = mu
+        nxt[1, :] += 0.01 * nxt[8, :]
+        return nxt
+
+    final = experiment.predictdynamics(batch, 4, [tr["Xtest"] for tr in trials], 3, step_fn)
+    for t, tr in enumerate(trials):
+        gps = []
+        for k in range(4):
+            kernel = gprb.SEArd(np.log(params[1:]), np.log(params[0]))
+            gp = gprb.GP(tr["X"], tr["Y"][k], gprb.MeanZero(), kernel)
+            gprb.optimize(gp, gprb.LBFGS(linesearch=gprb.BackTracking(order=2)), opts)
+            gps.append(gp)
+            np.testing.assert_allclose(gp.get_params(), batch.gps[4 * t + k].get_params(), rtol=1e-9, atol=1e-12)
+        for s in range(3):
+            state = tr["Xtest"][:, s].copy()
+            for _ in range(3):
+                obs = state.reshape(-1, 1)
+                mu = np.array([gprb.predict_y(gp, obs)[0][0] for gp in gps])
+                state = step_fn(t, obs, mu[:, None])[:, 0]
+            np.testing.assert_allclose(final[t][:, s], state, rtol=1e-9, atol=1e-12)
