@@ -39,6 +39,7 @@ static void free_batch(gprb_batch* b) {
   cudaFree(b->Dinv); cudaFree(b->DinvT); cudaFree(b->KinvD); cudaFree(b->alpha); cudaFree(b->zbuf); cudaFree(b->jitter);
   cudaFree(b->logdet_part); cudaFree(b->fail); cudaFree(b->mll); cudaFree(b->grad);
   cudaFree(b->grad_part); cudaFree(b->list);
+  cudaFree(b->pX); cudaFree(b->pms); cudaFree(b->pmu); cudaFree(b->pvar); cudaFree(b->pT); cudaFree(b->pmupart);
   if (b->list_host) cudaFreeHost(b->list_host);
   if (b->fail_host) cudaFreeHost(b->fail_host);
   if (b->stage_host) cudaFreeHost(b->stage_host);
@@ -237,11 +238,14 @@ int gprb_init(gprb_ctx** out, int device) {
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
   c->clock_khz = khz;
   c->l2_bytes = prop.l2CacheSize;
+  cudaError_t se = cudaStreamCreateWithFlags(&c->upload, cudaStreamNonBlocking);
+  if (se != cudaSuccess) { delete c; return cuda_fail(se, "cudaStreamCreate(upload)", __FILE__, __LINE__); }
   *out = c;
   return GPRB_OK;
 }
 
 int gprb_destroy(gprb_ctx* ctx) {
+  if (ctx && ctx->upload) { cudaSetDevice(ctx->device); cudaStreamDestroy(ctx->upload); }
   delete ctx;
   return GPRB_OK;
 }
@@ -258,14 +262,25 @@ int gprb_device_info(gprb_ctx* ctx, int64_t out[4]) {
 int64_t gprb_launch_count(gprb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------
-static int dataset_upload(gprb_dataset* ds, const double* X, int64_t ldx) {
-  GPRB_CUDA(cudaSetDevice(ds->ctx->device));
-  GPRB_CUDA(cudaMemcpy2D(ds->X, sizeof(double) * ds->d, X, sizeof(double) * ldx, sizeof(double) * ds->d, ds->n,
-                         cudaMemcpyHostToDevice));
-  int rc = launch_transpose_inputs(ds->X, ds->Xt, (int)ds->n, (int)ds->npad, ds->d, 0);
+// Enqueue the upload of one dataset on the context's upload stream (no synchronisation).
+static int dataset_upload_async(gprb_dataset* ds, const double* X, int64_t ldx) {
+  cudaStream_t st = ds->ctx->upload;
+  if (ldx == ds->d)
+    GPRB_CUDA(cudaMemcpyAsync(ds->X, X, sizeof(double) * ds->d * ds->n, cudaMemcpyHostToDevice, st));
+  else
+    GPRB_CUDA(cudaMemcpy2DAsync(ds->X, sizeof(double) * ds->d, X, sizeof(double) * ldx, sizeof(double) * ds->d, ds->n,
+                                cudaMemcpyHostToDevice, st));
+  int rc = launch_transpose_inputs(ds->X, ds->Xt, (int)ds->n, (int)ds->npad, ds->d, st);
   if (rc) return rc;
   ds->ctx->launches++;
-  GPRB_CUDA(cudaStreamSynchronize(0));
+  return 0;
+}
+
+static int dataset_upload(gprb_dataset* ds, const double* X, int64_t ldx) {
+  GPRB_CUDA(cudaSetDevice(ds->ctx->device));
+  int rc = dataset_upload_async(ds, X, ldx);
+  if (rc) return rc;
+  GPRB_CUDA(cudaStreamSynchronize(ds->ctx->upload));
   return 0;
 }
 
@@ -296,6 +311,24 @@ int gprb_dataset_update(gprb_dataset* ds, const double* X, int64_t ldx) {
   return dataset_upload(ds, X, ldx);
 }
 
+int gprb_datasets_update(gprb_ctx* ctx, int32_t count, gprb_dataset* const* ds, const double* const* X, int64_t ldx) {
+  GPRB_REQUIRE(ctx && ds && X && count >= 0, "gprb_datasets_update: bad argument");
+  for (int i = 0; i < count; ++i) {
+    GPRB_REQUIRE(ds[i] && X[i], "gprb_datasets_update: NULL dataset or matrix");
+    GPRB_REQUIRE(ds[i]->ctx == ctx, "gprb_datasets_update: dataset belongs to another context");
+    GPRB_REQUIRE(ldx >= ds[i]->d, "gprb_datasets_update: ldx < d");
+  }
+  GPRB_CUDA(cudaSetDevice(ctx->device));
+  // all copies and transposes are queued back to back (truly asynchronous when the host matrices are page-locked),
+  // one synchronisation at the end keeps the "synchronous on return" contract
+  for (int i = 0; i < count; ++i) {
+    int rc = dataset_upload_async(ds[i], X[i], ldx);
+    if (rc) return rc;
+  }
+  GPRB_CUDA(cudaStreamSynchronize(ctx->upload));
+  return GPRB_OK;
+}
+
 int gprb_dataset_destroy(gprb_dataset* ds) {
   if (!ds) return GPRB_OK;
   cudaFree(ds->X); cudaFree(ds->Xt);
@@ -305,7 +338,6 @@ int gprb_dataset_destroy(gprb_dataset* ds) {
 
 // ------------------------------------------------------------------------------------------------
 static int upload_targets(gprb_batch* b, const double* ymm) {
-  GPRB_CUDA(cudaMemsetAsync(b->ymm, 0, sizeof(double) * b->npad * b->B, b->stream[0]));
   GPRB_CUDA(cudaMemcpy2DAsync(b->ymm, sizeof(double) * b->npad, ymm, sizeof(double) * b->n, sizeof(double) * b->n, b->B,
                               cudaMemcpyHostToDevice, b->stream[0]));
   GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
@@ -367,6 +399,7 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
         (e = cudaMemcpy(b->Xtptr, xtp.data(), sizeof(double*) * B, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemset(b->theta, 0, sizeof(double) * B * b->P)) != cudaSuccess ||
         (e = cudaMemset(b->jitter, 0, sizeof(double) * B)) != cudaSuccess ||
+        (e = cudaMemset(b->ymm, 0, sizeof(double) * b->npad * B)) != cudaSuccess ||  // zero padding, written once
         (e = cudaMemset(b->fail, 0, sizeof(int32_t) * B)) != cudaSuccess) {
       rc = cuda_fail(e, "batch init copies", __FILE__, __LINE__);
       break;
@@ -466,6 +499,15 @@ int gprb_eval_device(gprb_batch* b, const double* theta_dev, double* mll_dev, do
 }
 
 // ------------------------------------------------------------------------------------------------
+static int ensure_doubles(double** p, size_t* cap, size_t need) {
+  if (*p && *cap >= need) return 0;
+  cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  int rc = dev_alloc(p, need);
+  if (!rc) *cap = need;
+  return rc;
+}
+
 int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_stride, const double* mstar, double* mu,
                  double* var) {
   GPRB_REQUIRE(b && Xstar && mu, "gprb_predict: NULL argument");
@@ -474,46 +516,54 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
     GPRB_REQUIRE(b->state_ok[i], "gprb_predict: a GP has no evaluated state - call gprb_eval or gprb_optimize first");
   GPRB_REQUIRE(xstar_stride == 0 || xstar_stride >= m * b->d, "gprb_predict: xstar_stride must be 0 or >= d*m");
   GPRB_CUDA(cudaSetDevice(b->ctx->device));
-  const int B = b->B;
+  const int B = b->B, J = b->J;
   cudaStream_t st = b->stream[0];
-  int ninv = 0;
-  if (var)
-    for (int i = 0; i < B; ++i)
-      if (!b->v_ok[i]) b->list_host[ninv++] = i;
-  if (ninv > 0) {
-    // variance needs L^-1: run the TRTRI rows on the resident factors that lack it
-    int rc = upload_list(b, ninv);
-    if (rc) return rc;
-    const int J = b->J;
-    GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->KinvD, b->list, b->npad * b->npad, (int64_t)J * NB * NB,
-                (int)b->npad, J, 0, GEMM_TRTRI_ROW, (int)((b->n + KT - 1) / KT * KT)};
-    for (int i = 1; i < J; ++i) {
-      ga.step = i;
-      if ((rc = launch_tile_gemm(ga, i, ninv, st))) return rc;
+  const size_t nx = (size_t)(xstar_stride ? xstar_stride * (B - 1) + m * b->d : m * b->d);
+  int rc;
+  if ((rc = ensure_doubles(&b->pX, &b->pX_cap, nx)) || (rc = ensure_doubles(&b->pmu, &b->pmu_cap, (size_t)B * m))) return rc;
+  if (mstar && (rc = ensure_doubles(&b->pms, &b->pms_cap, (size_t)B * m))) return rc;
+  if (var && (rc = ensure_doubles(&b->pvar, &b->pvar_cap, (size_t)B * m))) return rc;
+  GPRB_CUDA(cudaMemcpyAsync(b->pX, Xstar, sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+  if (mstar) GPRB_CUDA(cudaMemcpyAsync(b->pms, mstar, sizeof(double) * B * m, cudaMemcpyHostToDevice, st));
+
+  // GEMV-like path: few test columns and the triangular inverse already resident (the last evaluation had a gradient)
+  bool all_v = true;
+  for (int i = 0; i < B; ++i) all_v = all_v && b->v_ok[i];
+  const size_t small_smem = ((size_t)8 * b->npad + 8 * MAX_D + MAX_D + 8) * sizeof(double);
+  if (var && m <= 8 && all_v && small_smem <= 227 * 1024) {
+    PredictArgs pa{b->Xptr, b->theta, b->alpha, b->Lm, b->DinvT, b->pX, mstar ? b->pms : nullptr, b->pmu, b->pvar,
+                   xstar_stride, b->npad * b->npad, (int64_t)J * NB * NB, (int)b->n, (int)b->npad, b->d, (int)m, b->kind};
+    if ((rc = launch_predict(pa, B, st))) return rc;
+    b->ctx->launches++;
+  } else {
+    if (!b->pmupart && (rc = dev_alloc(&b->pmupart, (size_t)B * J * PT))) return rc;
+    if (var && !b->pT && (rc = dev_alloc(&b->pT, (size_t)B * b->npad * PT))) return rc;
+    const int nv = (int)((b->n + KT - 1) / KT * KT);
+    for (int64_t s0 = 0; s0 < m; s0 += PT) {
+      PredictTileArgs ta{b->Xtptr, b->theta, b->alpha, b->pX, mstar ? b->pms : nullptr, var ? b->pT : nullptr, b->pmupart,
+                         b->pmu, var ? b->pvar : nullptr, xstar_stride, (int)b->n, (int)b->npad, b->d, J, (int)m, b->kind,
+                         (int)s0, (int)std::min<int64_t>(PT, m - s0)};
+      if ((rc = launch_predict_cross(ta, B, st))) return rc;
+      b->ctx->launches++;
+      if (var) {
+        // L^-1 K*: one launch per block row, B tiles of 128 x 128 each (PDMats whiten! as a blocked substitution)
+        GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->KinvD, nullptr, b->npad * b->npad, (int64_t)J * NB * NB,
+                    (int)b->npad, J, 0, GEMM_FWD_ROW, nv};
+        ga.Tm = b->pT; ga.t_stride = b->npad * PT; ga.ldt = PT;
+        for (int i = 0; i < J; ++i) {
+          ga.step = i;
+          if ((rc = launch_tile_gemm(ga, 1, B, st))) return rc;
+          b->ctx->launches++;
+        }
+      }
+      if ((rc = launch_predict_finish(ta, B, st))) return rc;
       b->ctx->launches++;
     }
-    for (int k = 0; k < ninv; ++k) b->v_ok[b->list_host[k]] = 1;
   }
-  const size_t nx = (size_t)(xstar_stride ? xstar_stride * (B - 1) + m * b->d : m * b->d);
-  double *dX = nullptr, *dms = nullptr, *dmu = nullptr, *dvar = nullptr;
-  int rc = 0;
-  do {
-    if ((rc = dev_alloc(&dX, nx)) || (rc = dev_alloc(&dmu, (size_t)B * m))) break;
-    if (mstar && (rc = dev_alloc(&dms, (size_t)B * m))) break;
-    if (var && (rc = dev_alloc(&dvar, (size_t)B * m))) break;
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(dX, Xstar, sizeof(double) * nx, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D Xstar", __FILE__, __LINE__); break; }
-    if (mstar && (e = cudaMemcpyAsync(dms, mstar, sizeof(double) * B * m, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "H2D mstar", __FILE__, __LINE__); break; }
-    PredictArgs pa{b->Xptr, b->theta, b->alpha, b->Lm, b->DinvT, dX, dms, dmu, dvar, xstar_stride,
-                   b->npad * b->npad, (int64_t)b->J * NB * NB, (int)b->n, (int)b->npad, b->d, (int)m, b->kind};
-    if ((rc = launch_predict(pa, B, st))) break;
-    b->ctx->launches++;
-    if ((e = cudaMemcpyAsync(mu, dmu, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H mu", __FILE__, __LINE__); break; }
-    if (var && (e = cudaMemcpyAsync(var, dvar, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "D2H var", __FILE__, __LINE__); break; }
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "predict sync", __FILE__, __LINE__); break; }
-  } while (0);
-  cudaFree(dX); cudaFree(dms); cudaFree(dmu); cudaFree(dvar);
-  return rc;
+  GPRB_CUDA(cudaMemcpyAsync(mu, b->pmu, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
+  if (var) GPRB_CUDA(cudaMemcpyAsync(var, b->pvar, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
+  GPRB_CUDA(cudaStreamSynchronize(st));
+  return GPRB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

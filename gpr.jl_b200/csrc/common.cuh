@@ -41,6 +41,7 @@ struct gprb_ctx {
   int clock_khz = 0;
   int64_t l2_bytes = 0;
   int64_t launches = 0;
+  cudaStream_t upload = nullptr;  // dataset uploads + input transposes (non-blocking stream)
 };
 
 struct gprb_dataset {
@@ -96,6 +97,11 @@ struct gprb_batch {
   std::vector<uint8_t> inv_ok;    // per GP: K^-1 resident in A (last evaluation was value+gradient)
   std::vector<uint8_t> v_ok;      // per GP: V = L^-T resident in the upper tiles of Lm (TRTRI stage done)
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // prediction scratch, allocated on first use and kept (grow-only): staged test inputs / prior means / outputs,
+  // the right-hand-side block T [B][npad][PT] of the variance substitution and the per-block mean partials [B][J][PT]
+  double* pX = nullptr; double* pms = nullptr; double* pmu = nullptr; double* pvar = nullptr;
+  double* pT = nullptr; double* pmupart = nullptr;
+  size_t pX_cap = 0, pms_cap = 0, pmu_cap = 0, pvar_cap = 0;
   std::vector<cudaEvent_t> gemm_ev;  // profiling: start/stop pairs around every tile-GEMM launch
   int gemm_ev_used = 0;
 };

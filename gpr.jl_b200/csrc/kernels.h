@@ -5,7 +5,7 @@
 
 namespace gprb {
 
-enum { GEMM_CHOL_DIAG = 0, GEMM_CHOL_COL = 1, GEMM_TRTRI_ROW = 2, GEMM_LAUUM = 3 };
+enum { GEMM_CHOL_DIAG = 0, GEMM_CHOL_COL = 1, GEMM_TRTRI_ROW = 2, GEMM_LAUUM = 3, GEMM_FWD_ROW = 4 };
 
 struct GemmArgs {
   const double* Lm;     // operand matrices [B][npad*npad]
@@ -18,6 +18,11 @@ struct GemmArgs {
   int64_t mat_stride, dinv_stride;
   int npad, J, step, mode;
   int nv;               // n rounded up to 16: rows / k beyond it are padding that is neither computed nor read
+  // GEMM_FWD_ROW only: the right-hand-side block T [B][npad][ldt] (row r of T contiguous over the test columns);
+  // it is the B operand, the Cin source and the output at once (block row `step` is solved in place)
+  double* Tm = nullptr;
+  int64_t t_stride = 0;
+  int ldt = 0;
 };
 
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream);
@@ -101,6 +106,26 @@ struct PredictArgs {
   int64_t xstar_stride, mat_stride, dinv_stride;
   int n, npad, d, m, kind;
 };
-int launch_predict(const PredictArgs& a, int B, cudaStream_t stream);
+int launch_predict(const PredictArgs& a, int B, cudaStream_t stream);  // small-m path (needs V resident)
+
+// Tiled path: cross-covariances of one chunk of <= 128 test columns -> T[B][npad][PT] (+ per-block mean partials),
+// then the forward substitution L^-1 K* runs as GEMM_FWD_ROW launches and k_predict_finish reduces.
+constexpr int PT = 128;  // test columns per chunk (row length of T)
+struct PredictTileArgs {
+  const double* const* Xt;  // [B] transposed training inputs Xt[d][npad]
+  const double* theta;
+  const double* alpha;
+  const double* Xstar;      // d x m (+ b * xstar_stride)
+  const double* mstar;      // [B][m] or nullptr
+  double* T;                // [B][npad][PT] or nullptr (mean only)
+  double* mupart;           // [B][J][PT]
+  double* mu;               // [B][m]
+  double* var;              // [B][m] or nullptr
+  int64_t xstar_stride;
+  int n, npad, d, J, m, kind;
+  int s0, mc;               // chunk: test columns s0 .. s0 + mc
+};
+int launch_predict_cross(const PredictTileArgs& a, int B, cudaStream_t stream);
+int launch_predict_finish(const PredictTileArgs& a, int B, cudaStream_t stream);
 
 }  // namespace gprb

@@ -1,7 +1,10 @@
 // K6 posterior prediction (reference call examples/utils/predictdynamics.jl:13):
 //   k*_r = k(X[:,r], x*) ;  mu* = m(x*) + k*' alpha ;  var* = max(s_f^2 - |L^-1 k*|^2, 0) + exp(2 logNoise)
-// One CTA handles PS test columns of one GP: cross-covariances are built once into shared memory, the mean is
-// a fused dot product, and the variance streams the triangular inverse once per CTA (8 test columns share every element).
+// Two paths:
+//   k_predict        (m <= 8 with the triangular inverse V resident): one CTA handles PS test columns of one GP,
+//                    cross-covariances in shared memory, fused mean dot, variance streams V once (GEMV-like, HBM bound)
+//   k_predict_cross + GEMM_FWD_ROW tiles + k_predict_finish   (everything else): chunks of 128 test columns, the
+//                    variance is the blocked forward substitution L^-1 K* on the DMMA pipe (FP64 bound, n^2 flop/sample)
 #include "common.cuh"
 #include "kernels.h"
 
@@ -128,6 +131,140 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
     const double tot = block_sum(lane == 0 ? q[s] : 0.0, red);
     if (threadIdx.x == 0 && s < ns) g.var[(int64_t)gp * g.m + s0 + s] = fmax(sf2 - tot, 0.0) + sn2;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tiled path (any m, any n): cross-covariance block + mean partials, then L^-1 K* as DMMA tiles (tilegemm.cu,
+// GEMM_FWD_ROW) and a finishing reduction.  Follows the reference's whiten! exactly: a forward substitution with
+// the factor, no explicit inverse needed, so it also runs on a value-only state (after optimize!).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PC_THREADS = 256;
+
+// grid (J, B): CTA = 128 training rows x one chunk of <= 128 test columns of one GP.
+// lane -> test column (4 groups of 32), warp -> training row; T row r is written contiguously over the columns.
+template <int KIND>
+__global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = g.d;
+  double* Xi = reinterpret_cast<double*>(smem_raw);  // [d][NB]   training tile, one row per input dimension
+  double* xsT = Xi + d * NB;                          // [d][PT]   test columns, transposed, zero padded
+  double* w = xsT + d * PT;                           // [MAX_D]
+  double* red = w + MAX_D;                            // [8][PT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 8 * PT);
+  const int gp = blockIdx.y, ib = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* th = g.theta + (int64_t)gp * (d + 2);
+  const double* Xt = g.Xt[gp];
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(d * NB * sizeof(double)));
+  __syncthreads();
+  for (int p = threadIdx.x; p < d; p += PC_THREADS)
+    bulk_g2s(Xi + p * NB, Xt + (int64_t)p * g.npad + (int64_t)ib * NB, NB * sizeof(double), bar);
+  const double* Xstar = g.Xstar + (int64_t)gp * g.xstar_stride + (int64_t)g.s0 * d;
+  for (int idx = threadIdx.x; idx < d * PT; idx += PC_THREADS) {
+    const int s = idx / d, p = idx - s * d;  // consecutive threads walk one test column: coalesced global reads
+    xsT[p * PT + s] = s < g.mc ? Xstar[(int64_t)s * d + p] : 0.0;
+  }
+  if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
+  mbar_wait(bar, 0);
+  __syncthreads();
+  const double sf2 = exp(2.0 * th[d + 1]);
+  const double* alpha = g.alpha + (int64_t)gp * g.npad;
+  const int nq = (g.mc + 31) / 32;  // active 32-column groups
+  double macc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int rl = warp; rl < NB; rl += PC_THREADS / 32) {
+    const int r = ib * NB + rl;
+    double r2[4] = {0.0, 0.0, 0.0, 0.0};
+    if (r < g.n) {
+      for (int p = 0; p < d; ++p) {
+        const double xv = Xi[p * NB + rl], wp = w[p];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nq) {
+            const double df = xv - xsT[p * PT + lane + 32 * q];
+            r2[q] = fma(wp, df * df, r2[q]);
+          }
+      }
+    }
+    const double ar = r < g.n ? alpha[r] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int s = lane + 32 * q;
+      const double kv = (r < g.n && s < g.mc) ? kcross<KIND>(r2[q], sf2) : 0.0;
+      if (g.T) g.T[((int64_t)gp * g.npad + r) * PT + s] = kv;
+      macc[q] = fma(kv, ar, macc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) red[warp * PT + lane + 32 * q] = macc[q];
+  __syncthreads();
+  if (threadIdx.x < PT) {
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < PC_THREADS / 32; ++k) sum += red[k * PT + threadIdx.x];
+    g.mupart[((int64_t)gp * g.J + ib) * PT + threadIdx.x] = sum;
+  }
+}
+
+// grid B, 512 threads: thread = (row partition, test column).  mu = sum of the block partials + m(x*);
+// var = max(s_f^2 - sum_r T(r,s)^2, 0) + exp(2 logNoise), fixed summation order.
+__global__ void __launch_bounds__(512) k_predict_finish(PredictTileArgs g) {
+  __shared__ double red[4][PT];
+  const int gp = blockIdx.x, s = threadIdx.x & (PT - 1), part = threadIdx.x >> 7;
+  const int d = g.d;
+  const double* th = g.theta + (int64_t)gp * (d + 2);
+  if (g.var) {
+    const double* T = g.T + (int64_t)gp * g.npad * PT + s;
+    const int per = (g.n + 3) / 4, r0 = part * per, r1 = min(g.n, r0 + per);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+      const double v0 = T[(int64_t)r * PT], v1 = T[(int64_t)(r + 1) * PT], v2 = T[(int64_t)(r + 2) * PT], v3 = T[(int64_t)(r + 3) * PT];
+      a0 = fma(v0, v0, a0); a1 = fma(v1, v1, a1); a2 = fma(v2, v2, a2); a3 = fma(v3, v3, a3);
+    }
+    for (; r < r1; ++r) { const double v = T[(int64_t)r * PT]; a0 = fma(v, v, a0); }
+    red[part][s] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (part != 0 || s >= g.mc) return;
+  const int64_t o = (int64_t)gp * g.m + g.s0 + s;
+  double mu = 0.0;
+  for (int ib = 0; ib < g.J; ++ib) mu += g.mupart[((int64_t)gp * g.J + ib) * PT + s];
+  g.mu[o] = mu + (g.mstar ? g.mstar[o] : 0.0);
+  if (g.var) {
+    const double q = (red[0][s] + red[1][s]) + (red[2][s] + red[3][s]);
+    g.var[o] = fmax(exp(2.0 * th[d + 1]) - q, 0.0) + exp(2.0 * th[0]);
+  }
+}
+
+int launch_predict_cross(const PredictTileArgs& a, int B, cudaStream_t stream) {
+  if (B <= 0 || a.mc <= 0) return 0;
+  const size_t smem = ((size_t)a.d * NB + (size_t)a.d * PT + MAX_D + 8 * PT) * sizeof(double) + 16;
+  dim3 grid(a.J, B);
+  cudaError_t e;
+#define GPRB_PC_CASE(K)                                                                                       \
+  e = cudaFuncSetAttribute(k_predict_cross<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_predict_cross)", __FILE__, __LINE__);     \
+  k_predict_cross<K><<<grid, PC_THREADS, smem, stream>>>(a);
+  switch (a.kind) {
+    case GPRB_KERNEL_SE_ARD: GPRB_PC_CASE(0) break;
+    case GPRB_KERNEL_MAT12_ARD: GPRB_PC_CASE(1) break;
+    case GPRB_KERNEL_MAT32_ARD: GPRB_PC_CASE(2) break;
+    default: GPRB_PC_CASE(3) break;
+  }
+#undef GPRB_PC_CASE
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_predict_cross launch", __FILE__, __LINE__);
+  return 0;
+}
+
+int launch_predict_finish(const PredictTileArgs& a, int B, cudaStream_t stream) {
+  if (B <= 0 || a.mc <= 0) return 0;
+  k_predict_finish<<<B, 512, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_predict_finish launch", __FILE__, __LINE__);
+  return 0;
 }
 
 int launch_predict(const PredictArgs& a, int B, cudaStream_t stream) {

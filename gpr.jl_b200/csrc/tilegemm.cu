@@ -13,6 +13,8 @@
 //   CHOL_COL   L(i,j)   = [K(i,j) - sum_{k<j} L(i,k) L(j,k)^T] * inv(L_jj)^T      -> Lm(i,j)   i > j = step
 //   TRTRI_ROW  W(i,j)   = -inv(L_ii) * sum_{k=j}^{i-1} L(i,k) W(k,j)   stored as V(j,i) = W(i,j)^T, i = step
 //   LAUUM      Kinv(i,j) = sum_{k>=i} V(i,k) V(j,k)^T  (i >= j)  -> upper tile (j,i) of A (un-transposed) / KinvD(i)
+//   FWD_ROW    T(i,:)   = inv(L_ii) * [T(i,:) - sum_{k<i} L(i,k) T(k,:)]   in place in the right-hand-side block
+//              (blocked forward substitution L^-1 K* of the predictive variance, PDMats whiten!), i = step
 // where V = L^-T lives in the strictly-upper tiles of Lm and its diagonal blocks in DinvT.
 #include "common.cuh"
 #include "kernels.h"
@@ -49,6 +51,8 @@ __device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int b
     tc.i = step + 1 + bx; tc.j = step; tc.kb0 = 0; tc.kb1 = step; tc.use_cin = true; tc.post = 1; tc.rblk = step;
   } else if (mode == GEMM_TRTRI_ROW) {
     tc.i = step; tc.j = bx; tc.kb0 = bx; tc.kb1 = step; tc.b_diag_kb = bx; tc.post = 2; tc.rblk = step;
+  } else if (mode == GEMM_FWD_ROW) {
+    tc.i = step; tc.j = bx; tc.kb0 = 0; tc.kb1 = step; tc.use_cin = true; tc.post = 2; tc.rblk = step;
   } else {  // GEMM_LAUUM: bx enumerates (i, j), j <= i, row by row => longest k-range first
     int i = (int)((sqrt(8.0 * bx + 1.0) - 1.0) * 0.5);
     while ((i + 1) * (i + 2) / 2 <= bx) ++i;
@@ -113,7 +117,20 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
 
   // ---- T = Cin - acc (Cholesky) or acc
   const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * NB;
-  if (tc.use_cin) {
+  const bool fwd = g.mode == GEMM_FWD_ROW;
+  if (fwd) {  // T' = acc - T(i,:) so that the -inv(L_ii) post-multiply yields +inv(L_ii) (T(i,:) - acc)
+    const double* Tin = g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        if (RAGGED && mi >= mi_valid) continue;
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        const double2 v = *reinterpret_cast<const double2*>(Tin + cc + (int64_t)r * g.ldt);
+        acc[mi][ni][0] -= v.x;
+        acc[mi][ni][1] -= v.y;
+      }
+  } else if (tc.use_cin) {
     const double* Cin = g.Cin + (int64_t)gp * g.mat_stride + grow + gcol * npad;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
@@ -215,14 +232,16 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
         Cout[grow + r + (gcol + cc) * npad] = acc[mi][ni][0];
         Cout[grow + r + (gcol + cc + 1) * npad] = acc[mi][ni][1];
       }
-  } else {  // W(i,j) = -acc, stored transposed as V(j,i)
+  } else {  // W(i,j) = -acc, stored transposed as V(j,i); FWD_ROW: row r of the solved block, contiguous over the columns
+    double* outp = fwd ? g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt : Cout + gcol + grow * npad;
+    const int64_t ldo = fwd ? g.ldt : npad;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         if (RAGGED && mi >= mi_valid) continue;
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        *reinterpret_cast<double2*>(&Cout[gcol + cc + (grow + r) * npad]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+        *reinterpret_cast<double2*>(&outp[cc + r * ldo]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
       }
   }
 }
@@ -279,6 +298,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
       if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }
       else { srcA = Lm + (int64_t)tc.i * NB + (int64_t)kb * NB * npad; ldA = npad; }
       if (kb == tc.b_diag_kb) { srcB = DinvT + (int64_t)kb * NB * NB; ldB = NB; }
+      else if (g.mode == GEMM_FWD_ROW) { srcB = g.Tm + (int64_t)gp * g.t_stride + (int64_t)tc.j * NB + (int64_t)kb * NB * g.ldt; ldB = g.ldt; }
       else { srcB = Lm + (int64_t)tc.j * NB + (int64_t)kb * NB * npad; ldB = npad; }
       const int cend = (kb == g.J - 1) ? last_kb_chunks : NB / KT;
       for (int c = 0; c < cend; ++c) {

@@ -376,9 +376,13 @@ class GPBatch:
         """Re-upload inputs into the resident allocations: ``trials_X`` = list of new d x n arrays, one per distinct
         dataset in creation order; ``ymm`` (B, n) new targets (y - m(X))."""
         if trials_X is not None:
-            for h, Xn in zip(self._ds.values(), trials_X):
-                Xc = as_f64(np.asarray(Xn).T)
-                self.lib.check(self.lib.dll.gprb_dataset_update(h, _d(Xc), self.d))
+            hs = list(self._ds.values())
+            if len(trials_X) != len(hs):
+                raise ValueError(f"expected {len(hs)} input matrices, got {len(trials_X)}")
+            keep = [as_f64(np.asarray(Xn).T) for Xn in trials_X]  # views when Xn is already d x n column-major
+            harr = (C.c_void_p * len(hs))(*[h.value for h in hs])
+            parr = (C.POINTER(C.c_double) * len(hs))(*[_d(k) for k in keep])
+            self.lib.check(self.lib.dll.gprb_datasets_update(self.ctx.handle, len(hs), harr, parr, self.d))
         if ymm is not None:
             ymm = as_f64(ymm).reshape(self.B, self.n)
             self.lib.check(self.lib.dll.gprb_batch_set_targets(self.handle, _d(ymm)))

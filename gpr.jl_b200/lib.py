@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 EXPORTS = [
     "gprb_version", "gprb_last_error", "gprb_init", "gprb_destroy", "gprb_device_info",
-    "gprb_dataset_create", "gprb_dataset_update", "gprb_dataset_destroy",
+    "gprb_dataset_create", "gprb_dataset_update", "gprb_datasets_update", "gprb_dataset_destroy",
     "gprb_batch_create", "gprb_batch_set_targets", "gprb_batch_destroy",
     "gprb_eval", "gprb_eval_device", "gprb_lbfgs_default_opts", "gprb_optimize", "gprb_lbfgs_selftest", "gprb_predict",
     "gprb_get_K", "gprb_get_chol", "gprb_get_alpha", "gprb_get_Kinv",
@@ -66,6 +66,7 @@ class Library:
         L.gprb_device_info.argtypes = [_vp, C.POINTER(C.c_int64)]
         L.gprb_dataset_create.argtypes = [_vp, C.c_int64, C.c_int32, _dp, C.c_int64, C.POINTER(_vp)]
         L.gprb_dataset_update.argtypes = [_vp, _dp, C.c_int64]
+        L.gprb_datasets_update.argtypes = [_vp, C.c_int32, C.POINTER(_vp), C.POINTER(_dp), C.c_int64]
         L.gprb_dataset_destroy.argtypes = [_vp]
         L.gprb_batch_create.argtypes = [_vp, C.c_int32, C.POINTER(_vp), _dp, C.c_int32, C.POINTER(_vp)]
         L.gprb_batch_set_targets.argtypes = [_vp, _dp]

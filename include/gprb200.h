@@ -67,6 +67,9 @@ int gprb_device_info(gprb_ctx* ctx, int64_t out[4]);
 /* ---- dataset: X of one trial, uploaded once (CPnoise.jl:26 `reduce(hcat, ...)`) ------ */
 int gprb_dataset_create(gprb_ctx* ctx, int64_t n, int32_t d, const double* X, int64_t ldx, gprb_dataset** out);
 int gprb_dataset_update(gprb_dataset* ds, const double* X, int64_t ldx); /* same n, d; new samples */
+/* Re-upload `count` datasets in one call: all copies are queued back to back (asynchronous when the host matrices are
+ * page-locked) and the call returns after one synchronisation.  X[i] is d x n with leading dimension ldx. */
+int gprb_datasets_update(gprb_ctx* ctx, int32_t count, gprb_dataset* const* ds, const double* const* X, int64_t ldx);
 int gprb_dataset_destroy(gprb_dataset* ds);
 
 /* ---- batch: B independent GPs, GP b uses dataset ds[b] and targets ymm[:, b] ---------- */

@@ -149,6 +149,34 @@ def test_predict_parity_and_mean_only(gprb):
         np.testing.assert_allclose(mu3[b], mu[b, b:b + 5], rtol=1e-13)
 
 
+@pytest.mark.parametrize("system,n,m,kind", [("CP", 257, 130, "se"), ("P1", 100, 7, "se"), ("FB", 384, 40, "mat52"), ("P2", 640, 128, "se")])
+def test_predict_tiled_and_gemv_paths(gprb, system, n, m, kind):
+    """Both variance paths against the oracle's whiten! restatement: the tiled forward substitution (any m, value-only
+    state) and the GEMV-like path (m <= 8 with the triangular inverse resident)."""
+    from gpr_jl_b200 import data
+    tr = data.make_trial(system, n, seed=40 + n, n_test=m)
+    th = data.theta0(system, tr["X"])
+    th[1:-1] -= 1.0
+    G = tr["Y"].shape[0]
+    thetas = [np.tile(th, (G, 1)) + 0.03 * np.random.default_rng(m).standard_normal((G, th.size))]
+    batch = build_batch(gprb, [tr], thetas, kind=kind)
+    batch.eval(grad=False)
+    mu, var = batch.predict_y(tr["Xtest"])            # tiled path (no inverse resident)
+    X = np.ascontiguousarray(tr["X"].T)
+    ref = oracle_all([tr], thetas, kind=kind, grad=False)
+    for b, r in enumerate(ref):
+        m_o, v_o = go.predict(X, thetas[0][b], r["state"], np.ascontiguousarray(tr["Xtest"].T), kind=kind)
+        assert rel(mu[b], m_o) <= 1e-9
+        np.testing.assert_allclose(var[b], v_o, rtol=1e-9, atol=1e-13)
+    batch.eval(grad=True)                              # now V = L^-T is resident
+    mu2, var2 = batch.predict_y(tr["Xtest"][:, :5])    # GEMV-like path
+    np.testing.assert_allclose(mu2, mu[:, :5], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(var2, var[:, :5], rtol=1e-9, atol=1e-13)
+    mu3, none = batch.predict_y(tr["Xtest"], var=False)
+    assert none is None
+    np.testing.assert_allclose(mu3, mu, rtol=1e-12, atol=1e-14)
+
+
 def test_mean_function_plugin(gprb):
     """MeanDynamics-style host mean: only y - m(X) and m(x*) cross the boundary (src/mDynamics.jl:41-55)."""
     from gpr_jl_b200 import data
