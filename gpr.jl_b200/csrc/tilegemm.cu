@@ -54,13 +54,38 @@ __device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int b
   } else if (mode == GEMM_FWD_ROW) {
     tc.i = step; tc.j = bx; tc.kb0 = 0; tc.kb1 = step; tc.use_cin = true; tc.post = 2; tc.rblk = step;
   } else {  // GEMM_LAUUM: bx enumerates (i, j), j <= i, row by row => longest k-range first
-    int i = (int)((sqrt(8.0 * bx + 1.0) - 1.0) * 0.5);
+    int i = (int)((__fsqrt_rn(8.0f * bx + 1.0f) - 1.0f) * 0.5f);  // approximate, corrected by the two loops below
     while ((i + 1) * (i + 2) / 2 <= bx) ++i;
     while (i * (i + 1) / 2 > bx) --i;
     tc.i = i; tc.j = bx - i * (i + 1) / 2; tc.kb0 = i; tc.kb1 = J; tc.a_diag_kb = i;
     tc.b_diag_kb = (tc.j == i) ? i : -1;
   }
   return tc;
+}
+
+enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_MI4, SEL_MI6, SEL_NI2, SEL_TRI0, SEL_TRI4 };
+
+// One k-chunk (KT = 16) of a warp's 64x32 register tile restricted, at compile time, to the 8x8 blocks
+// (mi, ni) with mi < MI_LIM, ni < NI_LIM and mi >= ni + OFF: straight-line unpredicated DMMAs.
+template <int MI_LIM, int NI_LIM, int OFF>
+__device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* As, const double* Bs, int row0, int col0, int t) {
+#pragma unroll
+  for (int k4 = 0; k4 < KT / 4; ++k4) {
+    double a[8], b[4];
+    const double* ap = As + (k4 * 4 + t) * LDS_T + row0;
+    const double* bp = Bs + (k4 * 4 + t) * LDS_T + col0;
+#pragma unroll
+    for (int mi = 0; mi < MI_LIM; ++mi)
+      if (mi >= OFF) a[mi] = ap[mi * 8];
+#pragma unroll
+    for (int ni = 0; ni < NI_LIM; ++ni)
+      if (ni + OFF <= 7) b[ni] = bp[ni * 8];
+#pragma unroll
+    for (int mi = 0; mi < MI_LIM; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI_LIM; ++ni)
+        if (mi >= ni + OFF) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
 }
 
 // Consumer side of one tile (warps 0-7).  RAGGED = the tile touches the padded tail of the last block row:
@@ -87,26 +112,62 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
+  // Triangular operands: the leading k-block of TRTRI_ROW (B = inv(L_jj)) and of LAUUM (A = inv(L_ii)^T) is
+  // triangular, and CHOL_DIAG only needs the lower half of its symmetric tile.  The 8x8 DMMA blocks that would
+  // multiply structural zeros (or compute the unused upper half) are skipped through compile-time specialised
+  // chunk bodies (no per-DMMA predicates); with the {wn, 3-wn} / {wm 0, 1} warp pairing every SMSP keeps 9/16 of
+  // the work of those chunks.  Ragged tiles (last block row) keep the generic body.
+  int npred = 0;
+  if (!RAGGED) {
+    if (g.mode == GEMM_CHOL_DIAG) npred = nchunks;
+    else if (g.mode == GEMM_LAUUM || g.mode == GEMM_TRTRI_ROW) npred = min(nchunks, NB / KT);
+  }
+  const int diag_off = 4 * wn - 8 * wm;  // CHOL_DIAG: block (mi, ni) touches the lower triangle iff mi >= ni + diag_off
   {
     int stage = 0; uint32_t phase = 0;
     for (int c = 0; c < nchunks; ++c) {
       mbar_wait(&full[stage], phase);
       const double* As = stages + stage * STAGE_DOUBLES;
       const double* Bs = As + KT * LDS_T;
+      int sel = SEL_FULL;
+      if (c < npred) {
+        if (g.mode == GEMM_LAUUM) {             // rows r <= 16c + 15 of the upper-triangular A operand
+          const int mi_lim = 2 * c + 2 - 8 * wm;
+          sel = mi_lim <= 0 ? SEL_SKIP : mi_lim == 2 ? SEL_MI2 : mi_lim == 4 ? SEL_MI4 : mi_lim == 6 ? SEL_MI6 : SEL_FULL;
+        } else if (g.mode == GEMM_TRTRI_ROW) {  // columns <= 16c + 15 of the lower-triangular B operand
+          const int ni_lim = 2 * c + 2 - 4 * wn;
+          sel = ni_lim <= 0 ? SEL_SKIP : ni_lim == 2 ? SEL_NI2 : SEL_FULL;
+        } else {
+          sel = diag_off >= 8 ? SEL_SKIP : diag_off == 4 ? SEL_TRI4 : diag_off == 0 ? SEL_TRI0 : SEL_FULL;
+        }
+      }
+      switch (sel) {
+        case SEL_SKIP: break;
+        case SEL_MI2: chunk_mma<2, 4, -64>(acc, As, Bs, row0, col0, t); break;
+        case SEL_MI4: chunk_mma<4, 4, -64>(acc, As, Bs, row0, col0, t); break;
+        case SEL_MI6: chunk_mma<6, 4, -64>(acc, As, Bs, row0, col0, t); break;
+        case SEL_NI2: chunk_mma<8, 2, -64>(acc, As, Bs, row0, col0, t); break;
+        case SEL_TRI0: chunk_mma<8, 4, 0>(acc, As, Bs, row0, col0, t); break;
+        case SEL_TRI4: chunk_mma<8, 4, 4>(acc, As, Bs, row0, col0, t); break;
+        default:
+          if (!RAGGED) chunk_mma<8, 4, -64>(acc, As, Bs, row0, col0, t);
+          else {
 #pragma unroll
-      for (int k4 = 0; k4 < KT / 4; ++k4) {
-        double a[8], b[4];
-        const double* ap = As + (k4 * 4 + t) * LDS_T + row0;
-        const double* bp = Bs + (k4 * 4 + t) * LDS_T + col0;
+            for (int k4 = 0; k4 < KT / 4; ++k4) {
+              double a[8], b[4];
+              const double* ap = As + (k4 * 4 + t) * LDS_T + row0;
+              const double* bp = Bs + (k4 * 4 + t) * LDS_T + col0;
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi) a[mi] = ap[mi * 8];
+              for (int mi = 0; mi < 8; ++mi) a[mi] = ap[mi * 8];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
+              for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
-          if (!RAGGED || mi < mi_valid) {
+              for (int mi = 0; mi < 8; ++mi)
+                if (mi < mi_valid) {
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                  for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                }
+            }
           }
       }
       __syncwarp();
