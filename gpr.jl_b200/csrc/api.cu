@@ -144,6 +144,11 @@ static int run_pipeline(gprb_batch* b, int count, bool with_grad) {
       }
       b->stage_ms[6] = gsum;
       b->stage_ms[7] = b->gemm_ev_used / 2;
+      b->gemm_ms.clear();
+      for (int k = 0; k + 1 < b->gemm_ev_used; k += 2) {
+        GPRB_CUDA(cudaEventElapsedTime(&ms, b->gemm_ev[k], b->gemm_ev[k + 1]));
+        b->gemm_ms.push_back(ms);
+      }
     }
     return 0;
   }
@@ -427,6 +432,13 @@ int gprb_set_profiling(gprb_batch* b, int32_t on) {
   GPRB_REQUIRE(b, "gprb_set_profiling: NULL batch");
   b->profiling = on != 0;
   return GPRB_OK;
+}
+
+int gprb_last_gemm_launch_ms(gprb_batch* b, double* out, int32_t cap) {
+  GPRB_REQUIRE(b && (out || cap == 0), "gprb_last_gemm_launch_ms: NULL argument");
+  const int n = (int)b->gemm_ms.size();
+  for (int i = 0; i < n && i < cap; ++i) out[i] = b->gemm_ms[i];
+  return n;
 }
 
 int gprb_last_stage_ms(gprb_batch* b, double out[8]) {

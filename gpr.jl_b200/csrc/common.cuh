@@ -104,6 +104,7 @@ struct gprb_batch {
   size_t pX_cap = 0, pms_cap = 0, pmu_cap = 0, pvar_cap = 0;
   std::vector<cudaEvent_t> gemm_ev;  // profiling: start/stop pairs around every tile-GEMM launch
   int gemm_ev_used = 0;
+  std::vector<double> gemm_ms;  // per tile-GEMM launch time of the last profiled evaluation, launch order
 };
 
 // --------------------------------------------------------------------------------------

@@ -24,10 +24,12 @@ namespace gprb {
 constexpr int NSTAGE = 4;
 constexpr int STAGE_DOUBLES = 2 * KT * LDS_T;           // A + B operand chunk
 constexpr int RBUF_DOUBLES = KT * LDS_T;                // one chunk of the post-multiplier
+constexpr int NRBUF = 4;                                // ring depth of the post-multiplier chunks
 constexpr int N_CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = (N_CONSUMER_WARPS + 1) * 32;
+static_assert(2 * NSTAGE + 2 * NRBUF <= 16, "barrier block holds 16 mbarriers");
 static_assert(NSTAGE * STAGE_DOUBLES == NB * LDS_T, "T tile must exactly reuse the stage ring");
-constexpr size_t GEMM_SMEM = (size_t)(NSTAGE * STAGE_DOUBLES + 2 * RBUF_DOUBLES) * sizeof(double) + 16 * sizeof(uint64_t);
+constexpr size_t GEMM_SMEM = (size_t)(NSTAGE * STAGE_DOUBLES + NRBUF * RBUF_DOUBLES) * sizeof(double) + 16 * sizeof(uint64_t);
 
 struct TileCoord {
   int i, j;        // output tile (block row, block col)
@@ -68,12 +70,12 @@ enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_MI4, SEL_MI6, SEL_NI2, SEL_TRI0, SEL
 // One k-chunk (KT = 16) of a warp's 64x32 register tile restricted, at compile time, to the 8x8 blocks
 // (mi, ni) with mi < MI_LIM, ni < NI_LIM and mi >= ni + OFF: straight-line unpredicated DMMAs.
 template <int MI_LIM, int NI_LIM, int OFF>
-__device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* As, const double* Bs, int row0, int col0, int t) {
+__device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* ap, const double* bp) {
+  // ap / bp: this lane's fragment pointers at k4 = 0, i.e. base + t * LDS_T + row0 (resp. col0); both operands are
+  // k-major in smem with row stride LDS_T
 #pragma unroll
-  for (int k4 = 0; k4 < KT / 4; ++k4) {
+  for (int k4 = 0; k4 < KT / 4; ++k4, ap += 4 * LDS_T, bp += 4 * LDS_T) {
     double a[8], b[4];
-    const double* ap = As + (k4 * 4 + t) * LDS_T + row0;
-    const double* bp = Bs + (k4 * 4 + t) * LDS_T + col0;
 #pragma unroll
     for (int mi = 0; mi < MI_LIM; ++mi)
       if (mi >= OFF) a[mi] = ap[mi * 8];
@@ -86,6 +88,24 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* 
       for (int ni = 0; ni < NI_LIM; ++ni)
         if (mi >= ni + OFF) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
   }
+}
+
+// Dispatch one chunk to the specialised body `sel` (warp-uniform).
+__device__ __forceinline__ void chunk_dispatch(int sel, double (&acc)[8][4][2], const double* ap, const double* bp) {
+  switch (sel) {
+    case SEL_SKIP: break;
+    case SEL_MI2: chunk_mma<2, 4, -64>(acc, ap, bp); break;
+    case SEL_MI4: chunk_mma<4, 4, -64>(acc, ap, bp); break;
+    case SEL_MI6: chunk_mma<6, 4, -64>(acc, ap, bp); break;
+    case SEL_NI2: chunk_mma<8, 2, -64>(acc, ap, bp); break;
+    case SEL_TRI0: chunk_mma<8, 4, 0>(acc, ap, bp); break;
+    case SEL_TRI4: chunk_mma<8, 4, 4>(acc, ap, bp); break;
+    default: chunk_mma<8, 4, -64>(acc, ap, bp); break;
+  }
+}
+
+__device__ __forceinline__ int sel_rows(int mi_lim) {  // mi_lim is even (n is padded to 16-row chunks)
+  return mi_lim <= 0 ? SEL_SKIP : mi_lim == 2 ? SEL_MI2 : mi_lim == 4 ? SEL_MI4 : mi_lim == 6 ? SEL_MI6 : SEL_FULL;
 }
 
 // Consumer side of one tile (warps 0-7).  RAGGED = the tile touches the padded tail of the last block row:
@@ -116,60 +136,27 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   // triangular, and CHOL_DIAG only needs the lower half of its symmetric tile.  The 8x8 DMMA blocks that would
   // multiply structural zeros (or compute the unused upper half) are skipped through compile-time specialised
   // chunk bodies (no per-DMMA predicates); with the {wn, 3-wn} / {wm 0, 1} warp pairing every SMSP keeps 9/16 of
-  // the work of those chunks.  Ragged tiles (last block row) keep the generic body.
+  // the work of those chunks.  Ragged tiles (last block row) select the row-limited body for their mi_valid slabs.
   int npred = 0;
-  if (!RAGGED) {
-    if (g.mode == GEMM_CHOL_DIAG) npred = nchunks;
-    else if (g.mode == GEMM_LAUUM || g.mode == GEMM_TRTRI_ROW) npred = min(nchunks, NB / KT);
-  }
+  if (g.mode == GEMM_LAUUM) npred = min(nchunks, NB / KT);
+  else if (!RAGGED && g.mode == GEMM_CHOL_DIAG) npred = nchunks;
+  else if (!RAGGED && g.mode == GEMM_TRTRI_ROW) npred = NB / KT;
   const int diag_off = 4 * wn - 8 * wm;  // CHOL_DIAG: block (mi, ni) touches the lower triangle iff mi >= ni + diag_off
+  const int sel_plain = sel_rows(mi_valid);
   {
     int stage = 0; uint32_t phase = 0;
     for (int c = 0; c < nchunks; ++c) {
       mbar_wait(&full[stage], phase);
       const double* As = stages + stage * STAGE_DOUBLES;
-      const double* Bs = As + KT * LDS_T;
-      int sel = SEL_FULL;
+      int sel = sel_plain;
       if (c < npred) {
-        if (g.mode == GEMM_LAUUM) {             // rows r <= 16c + 15 of the upper-triangular A operand
-          const int mi_lim = 2 * c + 2 - 8 * wm;
-          sel = mi_lim <= 0 ? SEL_SKIP : mi_lim == 2 ? SEL_MI2 : mi_lim == 4 ? SEL_MI4 : mi_lim == 6 ? SEL_MI6 : SEL_FULL;
-        } else if (g.mode == GEMM_TRTRI_ROW) {  // columns <= 16c + 15 of the lower-triangular B operand
+        if (g.mode == GEMM_LAUUM) sel = sel_rows(min(mi_valid, 2 * c + 2 - 8 * wm));  // rows r <= 16c + 15 of the triangular A
+        else if (g.mode == GEMM_TRTRI_ROW) {                                          // columns <= 16c + 15 of the triangular B
           const int ni_lim = 2 * c + 2 - 4 * wn;
           sel = ni_lim <= 0 ? SEL_SKIP : ni_lim == 2 ? SEL_NI2 : SEL_FULL;
-        } else {
-          sel = diag_off >= 8 ? SEL_SKIP : diag_off == 4 ? SEL_TRI4 : diag_off == 0 ? SEL_TRI0 : SEL_FULL;
-        }
+        } else sel = diag_off >= 8 ? SEL_SKIP : diag_off == 4 ? SEL_TRI4 : diag_off == 0 ? SEL_TRI0 : SEL_FULL;
       }
-      switch (sel) {
-        case SEL_SKIP: break;
-        case SEL_MI2: chunk_mma<2, 4, -64>(acc, As, Bs, row0, col0, t); break;
-        case SEL_MI4: chunk_mma<4, 4, -64>(acc, As, Bs, row0, col0, t); break;
-        case SEL_MI6: chunk_mma<6, 4, -64>(acc, As, Bs, row0, col0, t); break;
-        case SEL_NI2: chunk_mma<8, 2, -64>(acc, As, Bs, row0, col0, t); break;
-        case SEL_TRI0: chunk_mma<8, 4, 0>(acc, As, Bs, row0, col0, t); break;
-        case SEL_TRI4: chunk_mma<8, 4, 4>(acc, As, Bs, row0, col0, t); break;
-        default:
-          if (!RAGGED) chunk_mma<8, 4, -64>(acc, As, Bs, row0, col0, t);
-          else {
-#pragma unroll
-            for (int k4 = 0; k4 < KT / 4; ++k4) {
-              double a[8], b[4];
-              const double* ap = As + (k4 * 4 + t) * LDS_T + row0;
-              const double* bp = Bs + (k4 * 4 + t) * LDS_T + col0;
-#pragma unroll
-              for (int mi = 0; mi < 8; ++mi) a[mi] = ap[mi * 8];
-#pragma unroll
-              for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
-#pragma unroll
-              for (int mi = 0; mi < 8; ++mi)
-                if (mi < mi_valid) {
-#pragma unroll
-                  for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-                }
-            }
-          }
-      }
+      chunk_dispatch(sel, acc, As + t * LDS_T + row0, As + (KT + t) * LDS_T + col0);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -258,26 +245,13 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   // Dinv is lower triangular: R[x][k] == 0 for k > x.  post 1: x = output column, post 2: x = output row.
   const int kmax = (tc.post == 1) ? (wn * 32 + 31) : min(wm * 64 + 63, rows_valid - 1);
   for (int c = 0; c < NB / KT; ++c) {
-    const int buf = c & 1;
-    mbar_wait(&rfull[buf], (c >> 1) & 1);
+    const int buf = c % NRBUF;
+    mbar_wait(&rfull[buf], (c / NRBUF) & 1);
     if (c * KT <= kmax) {
-      const double* Rs = rbuf + buf * RBUF_DOUBLES;
-#pragma unroll
-      for (int k4 = 0; k4 < KT / 4; ++k4) {
-        double a[8], b[4];
-        const double* ap = (tc.post == 1 ? Ts + (c * KT + k4 * 4 + t) * LDS_T : Rs + (k4 * 4 + t) * LDS_T) + row0;
-        const double* bp = (tc.post == 1 ? Rs + (k4 * 4 + t) * LDS_T : Ts + (c * KT + k4 * 4 + t) * LDS_T) + col0;
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi) a[mi] = ap[mi * 8];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = bp[ni * 8];
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
-          if (!RAGGED || mi < mi_valid) {
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-          }
-      }
+      const double* Rs = rbuf + buf * RBUF_DOUBLES + t * LDS_T;
+      const double* Tc = Ts + (c * KT + t) * LDS_T;
+      if (tc.post == 1) chunk_dispatch(sel_plain, acc, Tc + row0, Rs + col0);
+      else chunk_dispatch(sel_plain, acc, Rs + row0, Tc + col0);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rempty[buf]);
@@ -311,11 +285,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stages = reinterpret_cast<double*>(smem_raw);
   double* rbuf = stages + NSTAGE * STAGE_DOUBLES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + 2 * RBUF_DOUBLES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + NRBUF * RBUF_DOUBLES);
   uint64_t* full = bars;            // [NSTAGE]
   uint64_t* empty = bars + NSTAGE;  // [NSTAGE]
-  uint64_t* rfull = bars + 2 * NSTAGE;      // [2]
-  uint64_t* rempty = bars + 2 * NSTAGE + 2; // [2]
+  uint64_t* rfull = bars + 2 * NSTAGE;            // [NRBUF]
+  uint64_t* rempty = bars + 2 * NSTAGE + NRBUF;   // [NRBUF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
@@ -327,7 +301,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], N_CONSUMER_WARPS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], N_CONSUMER_WARPS); }
+    for (int s = 0; s < NRBUF; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], N_CONSUMER_WARPS); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -344,8 +318,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
     int stage = 0; uint32_t phase = 0;
     int rissued = 0;
     auto issue_r = [&](int c) {  // chunk c of the post-multiplier -> rbuf[c & 1]
-      const int buf = c & 1;
-      mbar_wait(&rempty[buf], ((c >> 1) & 1) ^ 1);
+      const int buf = c % NRBUF;
+      mbar_wait(&rempty[buf], ((c / NRBUF) & 1) ^ 1);
       if (lane == 0) mbar_expect_tx(&rfull[buf], KT * NB * sizeof(double));
       __syncwarp();
       if (lane < KT) {
@@ -353,7 +327,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
         bulk_g2s(rbuf + buf * RBUF_DOUBLES + lane * LDS_T, src, NB * sizeof(double), &rfull[buf]);
       }
     };
-    if (tc.post) { issue_r(0); issue_r(1); rissued = 2; }
+    if (tc.post) { for (; rissued < NRBUF; ++rissued) issue_r(rissued); }
     for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
       const double* srcA; const double* srcB; int64_t ldA, ldB;
       if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }

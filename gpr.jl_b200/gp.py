@@ -474,6 +474,19 @@ class GPBatch:
         self.lib.check(self.lib.dll.gprb_last_stage_ms(self.handle, _d(out)))
         return dict(zip(["assembly", "cholesky", "solve", "inverse", "gradient", "total", "gemm", "gemm_launches"], out.tolist()))
 
+    def last_gemm_launch_ms(self):
+        """Per tile-GEMM launch device time (ms) of the last profiled evaluation, labelled by mode and step."""
+        out = np.zeros(4 * (self.n // 128 + 2))
+        k = self.lib.dll.gprb_last_gemm_launch_ms(self.handle, _d(out), out.size)
+        J = (self.n + 127) // 128
+        labels = []
+        for j in range(J):
+            labels.append(("chol_diag", j))
+            if j + 1 < J:
+                labels.append(("chol_col", j))
+        labels += [("trtri_row", i) for i in range(1, J)] + [("lauum", 0)]
+        return [(m, st, float(t)) for (m, st), t in zip(labels[:k], out[:k])]
+
 
 def optimize(gp, method: LBFGS | None = None, options: Options | None = None):
     """``GaussianProcesses.optimize!(gp, method, options)``.  ``gp`` may be one GPE (reference call pattern) or a

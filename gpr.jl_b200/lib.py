@@ -15,7 +15,7 @@ EXPORTS = [
     "gprb_batch_create", "gprb_batch_set_targets", "gprb_batch_destroy",
     "gprb_eval", "gprb_eval_device", "gprb_lbfgs_default_opts", "gprb_optimize", "gprb_lbfgs_selftest", "gprb_predict",
     "gprb_get_K", "gprb_get_chol", "gprb_get_alpha", "gprb_get_Kinv",
-    "gprb_set_profiling", "gprb_last_stage_ms", "gprb_launch_count",
+    "gprb_set_profiling", "gprb_last_stage_ms", "gprb_last_gemm_launch_ms", "gprb_launch_count",
 ]
 
 
@@ -82,6 +82,7 @@ class Library:
             getattr(L, f).argtypes = [_vp, C.c_int32, _dp]
         L.gprb_set_profiling.argtypes = [_vp, C.c_int32]
         L.gprb_last_stage_ms.argtypes = [_vp, _dp]
+        L.gprb_last_gemm_launch_ms.argtypes = [_vp, _dp, C.c_int32]
         L.gprb_launch_count.argtypes = [_vp]
         L.gprb_launch_count.restype = C.c_int64
 

@@ -149,6 +149,9 @@ int gprb_get_Kinv(gprb_batch* batch, int32_t b, double* out /* n x n symmetric; 
  * Valid only when profiling was enabled with gprb_set_profiling(batch, 1) (single stream, stages serialised). */
 int gprb_set_profiling(gprb_batch* batch, int32_t on);
 int gprb_last_stage_ms(gprb_batch* batch, double out[8]);
+/* Device time of every tile-GEMM launch of the last profiled evaluation, in launch order (J x [CHOL_DIAG, CHOL_COL],
+ * then TRTRI_ROW 1..J-1, then LAUUM).  Writes at most `cap` values, returns the number of launches (>= 0). */
+int gprb_last_gemm_launch_ms(gprb_batch* batch, double* out, int32_t cap);
 /* Number of kernel launches issued by the library since the context was created. */
 int64_t gprb_launch_count(gprb_ctx* ctx);
 
