@@ -293,7 +293,7 @@ int gprb_dataset_create(gprb_ctx* ctx, int64_t n, int32_t d, const double* X, in
   GPRB_REQUIRE(ctx && X && out, "gprb_dataset_create: NULL argument");
   *out = nullptr;
   GPRB_REQUIRE(n >= 1 && n <= (1 << 20), "gprb_dataset_create: n out of range");
-  GPRB_REQUIRE(d >= 1 && d <= MAX_D, "gprb_dataset_create: d must be in 1..64");
+  GPRB_REQUIRE(d >= 1 && d <= MAX_D, "gprb_dataset_create: d must be in 1..62");
   GPRB_REQUIRE(ldx >= d, "gprb_dataset_create: ldx < d");
   GPRB_CUDA(cudaSetDevice(ctx->device));
   gprb_dataset* ds = new (std::nothrow) gprb_dataset();
@@ -379,7 +379,7 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
         (rc = dev_alloc(&b->alpha, (size_t)B * b->npad)) || (rc = dev_alloc(&b->zbuf, (size_t)B * b->npad)) ||
         (rc = dev_alloc(&b->jitter, B)) || (rc = dev_alloc(&b->logdet_part, (size_t)B * b->J)) ||
         (rc = dev_alloc(&b->fail, B)) || (rc = dev_alloc(&b->mll, B)) || (rc = dev_alloc(&b->grad, (size_t)B * b->P)) ||
-        (rc = dev_alloc(&b->grad_part, (size_t)B * ntiles * b->P)) || (rc = dev_alloc(&b->list, B)))
+        (rc = dev_alloc(&b->grad_part, (size_t)B * ntiles * GRAD_PARTS_PER_TILE * b->P)) || (rc = dev_alloc(&b->list, B)))
       break;
     b->stage_doubles = (int64_t)B * (b->P + 2);
     cudaError_t e;

@@ -13,7 +13,8 @@ namespace gprb {
 constexpr int NB = 128;        // tile edge of every blocked fp64 stage (Cholesky / TRTRI / LAUUM)
 constexpr int KT = 16;         // k-extent of one pipeline stage of the tile GEMM
 constexpr int LDS_T = NB + 4;  // padded smem row (doubles): (t*132 + g) mod 16 distinct over a half-warp
-constexpr int MAX_D = 64;      // 13 * bodies <= 52 in the reference (src/CState.jl:20); 64 leaves headroom
+constexpr int MAX_D = 62;      // 13 * bodies <= 52 in the reference (src/CState.jl:20); (MAX_D + 2) * 128 doubles fit the
+                               // 64 KB landing zone the gradient kernel reuses as its reduction buffer
 constexpr int MAX_JITTER = 10; // make_posdef! retries (GaussianProcesses 0.12.4)
 
 void set_error(const std::string& msg);

@@ -63,7 +63,8 @@ __device__ __forceinline__ void stage_inputs(const double* Xt, int npad, int d, 
   mbar_wait(bar, 0);
 }
 
-// r2[a][b] for the thread's 8x8 pair block: rows {2tx,2tx+1}+32*ra, cols {2ty,2ty+1}+32*cb.
+// r2[a][b] for the thread's 8x8 pair block: rows {2tx,2tx+1}+32*ra, cols {2ty,2ty+1}+(CW/4)*cb of a CW-wide column block.
+template <int CW>
 __device__ __forceinline__ void pair_r2(const double* Xi, const double* Xj, const double* w, int d, int tx, int ty,
                                         double (&r2)[8][8]) {
 #pragma unroll
@@ -76,7 +77,7 @@ __device__ __forceinline__ void pair_r2(const double* Xi, const double* Xj, cons
     for (int a = 0; a < 4; ++a) {
       const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
       xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
-      const double2 u = *reinterpret_cast<const double2*>(Xj + p * NB + 32 * a + 2 * ty);
+      const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + (CW / 4) * a + 2 * ty);
       xc[2 * a] = u.x; xc[2 * a + 1] = u.y;
     }
     const double wp = w[p];
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_assemble(AssembleArgs g) {
   }
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   double r2[8][8];
-  pair_r2(Xi, Xj, w, g.d, tx, ty, r2);
+  pair_r2<NB>(Xi, Xj, w, g.d, tx, ty, r2);
   double* A = g.A + (int64_t)gp * g.mat_stride;
   const int n = g.n;
 #pragma unroll
@@ -140,52 +141,107 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_assemble(AssembleArgs g) {
   }
 }
 
+// Gradient tiles.  One CTA (128 threads) = 128 rows x 32 columns of one lower tile; two CTAs per SM.
+// The K^-1 block, the K block and both input tiles are landed in shared memory by bulk async copies (TMA engine,
+// 1 KB per column), so all 98 KB of a block are in flight at once and the HBM latency of one CTA hides behind the
+// FP64 phase (3 d flops per pair) of the other.  (Register-destination loads cannot do this: with the 8x4 pair
+// block in registers the compiler keeps only a handful of loads in flight and the kernel becomes latency bound.)
+// Thread = 8 x 4 pairs: rows {2tx,2tx+1} + 32a (a < 4), columns {2ty,2ty+1} + 16cb (cb < 2).
+constexpr int GRAD_CW = NB / GRAD_PARTS_PER_TILE;  // 32
+constexpr int GRAD_THREADS = 128;
+static_assert(GRAD_CW == 32, "thread mapping below assumes 32-column blocks");
+
 template <int KIND>
-__global__ void __launch_bounds__(PW_THREADS, 1) k_grad_tiles(GradArgs g) {
+__global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
+  constexpr int CW = GRAD_CW, NT = GRAD_THREADS, NQ = NB / CW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = g.d;
-  double* Xi = reinterpret_cast<double*>(smem_raw);
-  double* Xj = Xi + d * NB;
-  double* w = Xj + d * NB;
-  double* red = w + MAX_D;                 // [(d + 2)][PW_THREADS]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + (d + 2) * PW_THREADS);
+  double* Ki = reinterpret_cast<double*>(smem_raw);  // [CW][NB] K^-1 block, column-major; reused as `red` afterwards
+  double* Kb = Ki + CW * NB;                          // [CW][NB] K block (SEArd only)
+  double* Xi = Kb + CW * NB;                          // [d][NB]
+  double* Xj = Xi + d * NB;                           // [d][CW]
+  double* w = Xj + d * CW;                            // [MAX_D]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(w + MAX_D);
+  double* red = Ki;                                   // [(d + 2)][NT] <= 2 * CW * NB doubles for d <= 62
   const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  const int tile = blockIdx.x / NQ, cq = blockIdx.x - tile * NQ;
   int ti, tj;
-  lower_tile(blockIdx.x, ti, tj);
+  lower_tile(tile, ti, tj);
+  constexpr bool REUSE_K = (KIND == GPRB_KERNEL_SE_ARD);
   const double* th = g.theta + (int64_t)gp * (d + 2);
-  if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
-  stage_inputs(g.Xt[gp], g.npad, d, ti, tj, Xi, Xj, bar);
+  const double* Xt = g.Xt[gp];
+  const int cbase = cq * CW;  // first column of this block inside the tile
+  const double* Kt = g.A + (int64_t)gp * g.mat_stride + (int64_t)ti * NB + (int64_t)(tj * NB + cbase) * g.npad;  // K block
+  const double* Kinv;  // K^-1 block: tile (ti,tj), ti > tj, lives un-transposed at tile position (tj,ti); diagonal tiles in KinvD
+  int64_t ldk;
+  if (ti == tj) { ldk = NB; Kinv = g.KinvD + (int64_t)gp * g.dinv_stride + (int64_t)ti * NB * NB + (int64_t)cbase * ldk; }
+  else { ldk = g.npad; Kinv = g.A + (int64_t)gp * g.mat_stride + (int64_t)tj * NB + ((int64_t)ti * NB + cbase) * ldk; }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
+  if (threadIdx.x == 0)
+    mbar_expect_tx(bar, (uint32_t)((d * (NB + CW) + (REUSE_K ? 2 : 1) * CW * NB) * sizeof(double)));
+  __syncthreads();
+  // 32 + 32 matrix columns, d + d input rows: one bulk copy each
+  for (int k = threadIdx.x; k < 2 * CW + 2 * d; k += NT) {
+    if (k < CW) bulk_g2s(Ki + k * NB, Kinv + (int64_t)k * ldk, NB * sizeof(double), bar);
+    else if (k < 2 * CW) { if (REUSE_K) bulk_g2s(Kb + (k - CW) * NB, Kt + (int64_t)(k - CW) * g.npad, NB * sizeof(double), bar); }
+    else if (k < 2 * CW + d) bulk_g2s(Xi + (k - 2 * CW) * NB, Xt + (int64_t)(k - 2 * CW) * g.npad + (int64_t)ti * NB, NB * sizeof(double), bar);
+    else bulk_g2s(Xj + (k - 2 * CW - d) * CW, Xt + (int64_t)(k - 2 * CW - d) * g.npad + (int64_t)tj * NB + cbase, CW * sizeof(double), bar);
+  }
+  if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
   const double sf2 = exp(2.0 * th[d + 1]);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double m[8][8];
-  // SEArd: dK/dll_p = K_f w_p Delta_p^2 and K_f,ij (i != j) is still resident in the lower tiles of A, so the
-  // distance pass and the exp are skipped; the Matern kernels need r itself and recompute it.
-  constexpr bool REUSE_K = (KIND == GPRB_KERNEL_SE_ARD);
-  if (!REUSE_K) pair_r2(Xi, Xj, w, d, tx, ty, m);  // m holds r2 for now
-  const double* Kt = g.A + (int64_t)gp * g.mat_stride + (int64_t)ti * NB + (int64_t)tj * NB * g.npad;  // K tile (ti,tj)
-  const double* Kinv;
-  int64_t ldk;
-  if (ti == tj) { Kinv = g.KinvD + (int64_t)gp * g.dinv_stride + (int64_t)ti * NB * NB; ldk = NB; }
-  else { Kinv = g.A + (int64_t)gp * g.mat_stride + (int64_t)tj * NB + (int64_t)ti * NB * g.npad; ldk = g.npad; }
   const double* alpha = g.alpha + (int64_t)gp * g.npad;
   const int n = g.n;
-  double s_sig = 0.0, s_tr = 0.0;
-  double ar[8];
+  double ar[8], ac[4];
 #pragma unroll
   for (int a = 0; a < 8; ++a) ar[a] = alpha[ti * NB + loc8(a, tx)];
 #pragma unroll
-  for (int b = 0; b < 8; ++b) {
-    const int cl = loc8(b, ty), c = tj * NB + cl;
-    const double ac = alpha[c];
+  for (int b = 0; b < 4; ++b) ac[b] = alpha[tj * NB + cbase + 16 * (b >> 1) + 2 * ty + (b & 1)];
+  mbar_wait(bar, 0);
+  __syncthreads();  // w visible
+  double m[8][4];
+  if (!REUSE_K) {  // Matern needs r itself: distances from the staged inputs (m holds r2 for now)
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) m[a][b] = 0.0;
+    for (int p = 0; p < d; ++p) {
+      double xr[8], xc[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
+        xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
+      }
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + 16 * cb + 2 * ty);
+        xc[2 * cb] = u.x; xc[2 * cb + 1] = u.y;
+      }
+      const double wp = w[p];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double df = xr[a] - xc[b];
+          m[a][b] = fma(wp, df * df, m[a][b]);
+        }
+    }
+  }
+  // phase 1: m_ij = (alpha_i alpha_j - Kinv_ij) g(r_ij).  SEArd: dK/dll_p = K_f w_p Delta_p^2 and K_f,ij (i != j) is
+  // still resident in the lower tiles of A, so the distance pass and the exp are skipped.
+  double s_sig = 0.0, s_tr = 0.0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int cl = 16 * (b >> 1) + 2 * ty + (b & 1), c = tj * NB + cbase + cl;
 #pragma unroll
     for (int a = 0; a < 8; a += 2) {
       const int rl = loc8(a, tx), r = ti * NB + rl;
-      const double2 kv = *reinterpret_cast<const double2*>(Kinv + rl + (int64_t)cl * ldk);
+      const double2 kv = *reinterpret_cast<const double2*>(Ki + cl * NB + rl);
       const double kin[2] = {kv.x, kv.y};
       double kst[2] = {0.0, 0.0};
       if (REUSE_K) {
-        const double2 ks = *reinterpret_cast<const double2*>(Kt + rl + (int64_t)cl * g.npad);
+        const double2 ks = *reinterpret_cast<const double2*>(Kb + cl * NB + rl);
         kst[0] = ks.x; kst[1] = ks.y;
       }
 #pragma unroll
@@ -194,7 +250,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_grad_tiles(GradArgs g) {
         double kf, gf;
         if (REUSE_K) { kf = (rr == c) ? sf2 : kst[e]; gf = kf; }
         else kfun<KIND>(m[a + e][b], sf2, kf, gf);
-        double q = ar[a + e] * ac - kin[e];
+        double q = ar[a + e] * ac[b] - kin[e];
         if (rr >= n || c >= n) { q = 0.0; kf = 0.0; gf = 0.0; }
         s_sig = fma(q, kf, s_sig);
         if (rr == c) s_tr += q;
@@ -202,39 +258,42 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_grad_tiles(GradArgs g) {
       }
     }
   }
-  // pass 2: per-dimension weighted sums; one scalar per (p, thread) parked in smem
+  __syncthreads();  // every thread is done with the landed blocks: the space becomes `red`
+  // phase 2 (FP64 pipe): per-dimension weighted sums; one scalar per (p, thread) parked in smem
   for (int p = 0; p < d; ++p) {
-    double xr[8], xc[8];
+    double xr[8], xc[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
       xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
-      const double2 u = *reinterpret_cast<const double2*>(Xj + p * NB + 32 * a + 2 * ty);
-      xc[2 * a] = u.x; xc[2 * a + 1] = u.y;
+    }
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + 16 * cb + 2 * ty);
+      xc[2 * cb] = u.x; xc[2 * cb + 1] = u.y;
     }
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int a = 0; a < 8; a += 2)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
+      for (int b = 0; b < 4; ++b) {
         const double d0 = xr[a] - xc[b], d1 = xr[a + 1] - xc[b];
         s0 = fma(m[a][b], d0 * d0, s0);
         s1 = fma(m[a + 1][b], d1 * d1, s1);
       }
-    red[p * PW_THREADS + threadIdx.x] = s0 + s1;
+    red[p * NT + threadIdx.x] = s0 + s1;
   }
-  red[d * PW_THREADS + threadIdx.x] = s_sig;
-  red[(d + 1) * PW_THREADS + threadIdx.x] = s_tr;
+  red[d * NT + threadIdx.x] = s_sig;
+  red[(d + 1) * NT + threadIdx.x] = s_tr;
   __syncthreads();
-  // fixed-order block reduction: warp v sums rows v, v+8, ...
+  // fixed-order block reduction: warp v sums rows v, v + 4, ...
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double wt = (ti == tj) ? 1.0 : 2.0;
-  const int ntiles = g.J * (g.J + 1) / 2;
-  double* part = g.part + ((int64_t)gp * ntiles + blockIdx.x) * (d + 2);
-  for (int row = warp; row < d + 2; row += PW_THREADS / 32) {
+  double* part = g.part + ((int64_t)gp * gridDim.x + blockIdx.x) * (d + 2);
+  for (int row = warp; row < d + 2; row += NT / 32) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < PW_THREADS / 32; ++k) s += red[row * PW_THREADS + lane + 32 * k];
+    for (int k = 0; k < NT / 32; ++k) s += red[row * NT + lane + 32 * k];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) {
@@ -249,7 +308,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_grad_tiles(GradArgs g) {
 __global__ void k_grad_reduce(GradArgs g) {
   const int gp = g.list ? g.list[blockIdx.x] : blockIdx.x;
   const int d = g.d, P = d + 2;
-  const int ntiles = g.J * (g.J + 1) / 2;
+  const int ntiles = g.J * (g.J + 1) / 2 * (NB / GRAD_CW);  // partial blocks written by k_grad_tiles
   const double* th = g.theta + (int64_t)gp * P;
   const double* part = g.part + (int64_t)gp * ntiles * P;
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
@@ -283,7 +342,7 @@ __global__ void k_add_jitter(const double* theta, double* jitter, const int32_t*
 }
 
 static size_t pw_smem(int d, bool grad) {
-  size_t doubles = (size_t)2 * d * NB + MAX_D + (grad ? (size_t)(d + 2) * PW_THREADS : 0);
+  size_t doubles = grad ? (size_t)2 * GRAD_CW * NB + (size_t)d * (NB + GRAD_CW) + MAX_D : (size_t)2 * d * NB + MAX_D;
   return doubles * sizeof(double) + 16;
 }
 
@@ -314,14 +373,18 @@ int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream) {
 int launch_grad(const GradArgs& a, int count, cudaStream_t stream) {
   if (count <= 0) return 0;
   const size_t smem = pw_smem(a.d, true);
-  dim3 grid(a.J * (a.J + 1) / 2, count);
+  dim3 grid(a.J * (a.J + 1) / 2 * (NB / GRAD_CW), count);
   int rc = 0;
+#define GPRB_GRAD_CASE(K)                                             \
+  rc = set_smem(k_grad_tiles<K>, smem);                               \
+  if (!rc) k_grad_tiles<K><<<grid, GRAD_THREADS, smem, stream>>>(a);
   switch (a.kind) {
-    case GPRB_KERNEL_SE_ARD: rc = set_smem(k_grad_tiles<0>, smem); if (!rc) k_grad_tiles<0><<<grid, PW_THREADS, smem, stream>>>(a); break;
-    case GPRB_KERNEL_MAT12_ARD: rc = set_smem(k_grad_tiles<1>, smem); if (!rc) k_grad_tiles<1><<<grid, PW_THREADS, smem, stream>>>(a); break;
-    case GPRB_KERNEL_MAT32_ARD: rc = set_smem(k_grad_tiles<2>, smem); if (!rc) k_grad_tiles<2><<<grid, PW_THREADS, smem, stream>>>(a); break;
-    default: rc = set_smem(k_grad_tiles<3>, smem); if (!rc) k_grad_tiles<3><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    case GPRB_KERNEL_SE_ARD: GPRB_GRAD_CASE(0) break;
+    case GPRB_KERNEL_MAT12_ARD: GPRB_GRAD_CASE(1) break;
+    case GPRB_KERNEL_MAT32_ARD: GPRB_GRAD_CASE(2) break;
+    default: GPRB_GRAD_CASE(3) break;
   }
+#undef GPRB_GRAD_CASE
   if (rc) return rc;
   k_grad_reduce<<<count, 64, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();

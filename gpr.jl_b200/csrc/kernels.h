@@ -71,6 +71,7 @@ struct SolveArgs {
 };
 int launch_solve(const SolveArgs& a, int count, cudaStream_t stream);
 
+constexpr int GRAD_PARTS_PER_TILE = 4;  // k_grad_tiles splits every 128x128 tile into 128 x 32 column blocks (one CTA each)
 // K5: fused gradient  d mll / d theta = 1/2 tr((alpha alpha' - K^-1) dK/dtheta), never materialising dK.
 struct GradArgs {
   const double* const* Xt;
@@ -78,7 +79,7 @@ struct GradArgs {
   const double* A;      // lower tiles: K (intact); strictly-upper tile (j,i): K^-1 tile (i,j), un-transposed
   const double* KinvD;  // [B][J][NB*NB] diagonal tiles of K^-1
   const double* alpha;
-  double* part;         // [B][ntiles][P + 1]
+  double* part;         // [B][ntiles * GRAD_PARTS_PER_TILE][P]
   double* grad;         // [B][P]
   const int32_t* fail;
   const int32_t* list;
