@@ -80,14 +80,16 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
           if (bad == 0) bad = j0 + c + 1;
           piv = 1.0;
         }
-        const double l = sqrt(piv);
-        const double inv = 1.0 / l;
-        logdet += log(l);
+        // one reciprocal square root instead of sqrt + divide + log on the serial critical path of the block
+        // (each is a long dependent instruction sequence); the logs are taken once per lane after the loop
+        const double inv = rsqrt(piv);
+        const double l = piv * inv;
         if (lane > c) D[c * LDS_T + lane] = v * inv;
         else if (lane == c) { D[c * LDS_T + c] = l; dinv32[c] = inv; }
         __syncwarp();
       }
       if (bad != 0 && lane == 0 && bad_col == 0) bad_col = bad;
+      logdet += log(D[lane * LDS_T + lane]);  // lane c holds log L_cc; warp-reduced once at the end of the kernel
       // L_dd straight to HBM (lower), zeros above the diagonal
       for (int c = 0; c < SB; ++c) T[(j0 + lane) + (int64_t)(j0 + c) * npad] = (lane >= c) ? D[c * LDS_T + lane] : 0.0;
       // W = inv(L_dd): lane c owns column c; W(r,c), r > c, is parked transposed at D(c,r) (strict upper part)
@@ -195,7 +197,11 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
     DinvT[idx] = (br <= bc) ? S[c * LDS_T + r] : 0.0;   // W^T(r,c)
     Dinv[idx] = (br >= bc) ? S[r * LDS_T + c] : 0.0;    // W(r,c) = W^T(c,r)
   }
-  if (tid == 0) g.logdet_part[(int64_t)gp * g.J + j] = logdet;
+  if (warp == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) logdet += __shfl_xor_sync(FULL, logdet, off);
+    if (lane == 0) g.logdet_part[(int64_t)gp * g.J + j] = logdet;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
