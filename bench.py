@@ -241,8 +241,15 @@ def main():
     peak, peak_src = fp64_peak()
     gemm_flops = float(B) * n ** 3  # potrf n^3/3 + inverse-from-factor 2n^3/3 (algorithmic, un-padded)
     achieved = gemm_flops / (st["gemm"] * 1e-3) / 1e12 if st["gemm"] > 0 else 0.0
+    traffic, traffic_src = None, None
+    if n == N_TRAIN and T == TRIALS:  # ncu dram__bytes_read+write per launch, captured at exactly this configuration
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_traffic.json (tools/traffic.sh: ncu dram bytes, mean of the 47 launches of one evaluation)"
+        except Exception:
+            pass
     roof = {"bound": "tensor", "kernel": "k_tile_gemm (fp64 DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "launches_per_step": int(st["gemm_launches"]), "flops_per_launch": gemm_flops / max(st["gemm_launches"], 1),
             "avg_launch_ms": st["gemm"] / max(st["gemm_launches"], 1),
             "stage_ms": {k: round(v, 3) for k, v in st.items() if k != "gemm_launches"},
