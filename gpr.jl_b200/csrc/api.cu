@@ -1,6 +1,7 @@
 // C ABI of libgprb200 (include/gprb200.h): handle management and the host-side orchestration of the
 // evaluation pipeline  assembly -> blocked Cholesky -> solves/mll -> inverse -> fused gradient.
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -69,10 +70,38 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
       b->gemm_ev.push_back(e);
     }
     cudaEventRecord(b->gemm_ev[b->gemm_ev_used], st);
+#ifdef GPRB_TIMELINE
+    // debug build only: per-tile phase timestamps of this launch, averaged and printed to stderr
+    static unsigned long long* tl_dev = nullptr;
+    const size_t tl_n = (size_t)count * ntiles * 8;
+    if (!tl_dev) cudaMalloc(&tl_dev, sizeof(unsigned long long) * 8 * 65536 * 16);
+    cudaMemsetAsync(tl_dev, 0, sizeof(unsigned long long) * tl_n, st);
+    GemmArgs a2 = a; a2.tl = tl_dev;
+    int r = launch_tile_gemm(a2, ntiles, count, st);
+    cudaEventRecord(b->gemm_ev[b->gemm_ev_used + 1], st);
+    b->gemm_ev_used += 2;
+    {
+      std::vector<unsigned long long> h(tl_n);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h.data(), tl_dev, sizeof(unsigned long long) * tl_n, cudaMemcpyDeviceToHost);
+      double ph[6] = {0, 0, 0, 0, 0, 0}, tot = 0; size_t cnt = 0;
+      for (size_t k = 0; k < tl_n; k += 8) {
+        const unsigned long long* t = &h[k];
+        if (!t[0] || !t[6]) continue;
+        unsigned long long prev = t[0];
+        for (int q = 1; q <= 6; ++q) { unsigned long long cur = t[q] ? t[q] : prev; ph[q - 1] += (double)(cur - prev); prev = cur; }
+        tot += (double)(t[6] - t[0]); ++cnt;
+      }
+      if (cnt) fprintf(stderr, "TL mode %d step %2d tiles %6zu  fill %6.2f main %7.2f cin %6.2f park %6.2f post %6.2f store %6.2f  total %7.2f us\n",
+                       a.mode, a.step, cnt, ph[0] / cnt / 1e3, ph[1] / cnt / 1e3, ph[2] / cnt / 1e3, ph[3] / cnt / 1e3, ph[4] / cnt / 1e3, ph[5] / cnt / 1e3, tot / cnt / 1e3);
+    }
+    return r;
+#else
     int r = launch_tile_gemm(a, ntiles, count, st);
     cudaEventRecord(b->gemm_ev[b->gemm_ev_used + 1], st);
     b->gemm_ev_used += 2;
     return r;
+#endif
   };
   if (prof) { b->gemm_ev_used = 0; cudaEventRecord(b->ev[0], st); }
   AssembleArgs aa{b->Xtptr, b->theta, b->jitter, b->A, b->fail, list, ms, (int)b->n, (int)b->npad, b->d, J, b->kind};

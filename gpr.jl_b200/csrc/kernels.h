@@ -23,6 +23,7 @@ struct GemmArgs {
   double* Tm = nullptr;
   int64_t t_stride = 0;
   int ldt = 0;
+  unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)
 };
 
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream);

@@ -21,6 +21,15 @@
 
 namespace gprb {
 
+// Debug timeline (build with -DGPRB_TIMELINE): warp 0 lane 0 of every tile records globaltimer at phase boundaries.
+#ifdef GPRB_TIMELINE
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GPRB_TL(k) do { if (g.tl && threadIdx.x == 0) g.tl[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = gtimer(); } while (0)
+#else
+#define GPRB_TL(k) do { } while (0)
+#endif
+
+
 constexpr int NSTAGE = 4;
 constexpr int STAGE_DOUBLES = 2 * KT * LDS_T;           // A + B operand chunk
 constexpr int RBUF_DOUBLES = KT * LDS_T;                // one chunk of the post-multiplier
@@ -126,11 +135,42 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   const int row0 = wm * 64 + gq;  // + mi*8
   const int col0 = wn * 32 + gq;  // + ni*8  (operand row index of B)
 
+  // The accumulators start at -Cin (Cholesky tiles: K(i,j); FWD_ROW: the right-hand-side block), loaded straight
+  // into the accumulator registers while the first operand chunks are still in flight: the 64 global loads per
+  // thread need no extra registers and their latency hides behind the pipeline fill.  After the k-loop
+  // acc = sum - Cin = -(Cin - sum); the sign is folded into the stores below.
+  const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * NB;
+  const bool fwd = g.mode == GEMM_FWD_ROW;
   double acc[8][4][2];
+  if (fwd) {
+    const double* Tin = g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt;
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        double2 v = make_double2(0.0, 0.0);
+        if (!RAGGED || mi < mi_valid) v = *reinterpret_cast<const double2*>(Tin + cc + (int64_t)r * g.ldt);
+        acc[mi][ni][0] = -v.x;
+        acc[mi][ni][1] = -v.y;
+      }
+  } else if (tc.use_cin) {
+    const double* Cin = g.Cin + (int64_t)gp * g.mat_stride + grow + gcol * npad;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        const bool ok = !RAGGED || mi < mi_valid;
+        acc[mi][ni][0] = ok ? -Cin[r + (int64_t)cc * npad] : 0.0;
+        acc[mi][ni][1] = ok ? -Cin[r + (int64_t)(cc + 1) * npad] : 0.0;
+      }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  }
 
   // Triangular operands: the leading k-block of TRTRI_ROW (B = inv(L_jj)) and of LAUUM (A = inv(L_ii)^T) is
   // triangular, and CHOL_DIAG only needs the lower half of its symmetric tile.  The 8x8 DMMA blocks that would
@@ -147,6 +187,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     int stage = 0; uint32_t phase = 0;
     for (int c = 0; c < nchunks; ++c) {
       mbar_wait(&full[stage], phase);
+      if (c == 0) GPRB_TL(1);
       const double* As = stages + stage * STAGE_DOUBLES;
       int sel = sel_plain;
       if (c < npred) {
@@ -163,40 +204,15 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     }
   }
 
-  // ---- T = Cin - acc (Cholesky) or acc
-  const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * NB;
-  const bool fwd = g.mode == GEMM_FWD_ROW;
-  if (fwd) {  // T' = acc - T(i,:) so that the -inv(L_ii) post-multiply yields +inv(L_ii) (T(i,:) - acc)
-    const double* Tin = g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt;
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        if (RAGGED && mi >= mi_valid) continue;
-        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        const double2 v = *reinterpret_cast<const double2*>(Tin + cc + (int64_t)r * g.ldt);
-        acc[mi][ni][0] -= v.x;
-        acc[mi][ni][1] -= v.y;
-      }
-  } else if (tc.use_cin) {
-    const double* Cin = g.Cin + (int64_t)gp * g.mat_stride + grow + gcol * npad;
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        if (RAGGED && mi >= mi_valid) continue;
-        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        acc[mi][ni][0] = Cin[r + (int64_t)cc * npad] - acc[mi][ni][0];
-        acc[mi][ni][1] = Cin[r + (int64_t)(cc + 1) * npad] - acc[mi][ni][1];
-      }
-  }
-
+  GPRB_TL(2);
+  GPRB_TL(3);
   double* Cout = g.Cout + (int64_t)gp * g.mat_stride;
   if (tc.post == 0) {
     // CHOL_DIAG: S(j,j) -> Lm(j,j).  LAUUM: K^-1(i,j), i > j, goes un-transposed into the free upper tile (j,i) of A
     // (K stays intact in the lower tiles for the gradient stage); diagonal tiles go to the KinvD side buffer.
     double* out = Cout + grow + gcol * npad;
     int64_t ldo = npad;
+    const double sgn = tc.use_cin ? -1.0 : 1.0;  // CHOL_DIAG: S = Cin - sum = -acc
     if (g.mode == GEMM_LAUUM) {
       if (tc.i != tc.j) out = Cout + gcol + grow * npad;
       else { out = g.KinvD + (int64_t)gp * g.dinv_stride + (int64_t)tc.i * NB * NB; ldo = NB; }
@@ -207,9 +223,10 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
       for (int ni = 0; ni < 4; ++ni) {
         if (RAGGED && mi >= mi_valid) continue;
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        out[r + (int64_t)cc * ldo] = acc[mi][ni][0];
-        out[r + (int64_t)(cc + 1) * ldo] = acc[mi][ni][1];
+        out[r + (int64_t)cc * ldo] = sgn * acc[mi][ni][0];
+        out[r + (int64_t)(cc + 1) * ldo] = sgn * acc[mi][ni][1];
       }
+    GPRB_TL(6);
     return;
   }
 
@@ -241,6 +258,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
   named_bar_sync(1, N_CONSUMER_WARPS * 32);
+  GPRB_TL(4);
 
   // Dinv is lower triangular: R[x][k] == 0 for k > x.  post 1: x = output column, post 2: x = output row.
   const int kmax = (tc.post == 1) ? (wn * 32 + 31) : min(wm * 64 + 63, rows_valid - 1);
@@ -256,6 +274,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     __syncwarp();
     if (lane == 0) mbar_arrive(&rempty[buf]);
   }
+  GPRB_TL(5);
 
   if (tc.post == 1) {
 #pragma unroll
@@ -264,10 +283,10 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
       for (int ni = 0; ni < 4; ++ni) {
         if (RAGGED && mi >= mi_valid) continue;
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
-        Cout[grow + r + (gcol + cc) * npad] = acc[mi][ni][0];
-        Cout[grow + r + (gcol + cc + 1) * npad] = acc[mi][ni][1];
+        Cout[grow + r + (gcol + cc) * npad] = -acc[mi][ni][0];      // parked operand was -(Cin - sum)
+        Cout[grow + r + (gcol + cc + 1) * npad] = -acc[mi][ni][1];
       }
-  } else {  // W(i,j) = -acc, stored transposed as V(j,i); FWD_ROW: row r of the solved block, contiguous over the columns
+  } else {  // W(i,j) = -acc, stored transposed as V(j,i); FWD_ROW (parked operand sum - T(i,:)): row r of the solved block
     double* outp = fwd ? g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt : Cout + gcol + grow * npad;
     const int64_t ldo = fwd ? g.ldt : npad;
 #pragma unroll
@@ -279,6 +298,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
         *reinterpret_cast<double2*>(&outp[cc + r * ldo]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
       }
   }
+  GPRB_TL(6);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
@@ -291,6 +311,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
   uint64_t* rfull = bars + 2 * NSTAGE;            // [NRBUF]
   uint64_t* rempty = bars + 2 * NSTAGE + NRBUF;   // [NRBUF]
 
+  GPRB_TL(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
   const TileCoord tc = tile_coord(g.mode, g.step, g.J, blockIdx.x);
@@ -327,7 +348,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
         bulk_g2s(rbuf + buf * RBUF_DOUBLES + lane * LDS_T, src, NB * sizeof(double), &rfull[buf]);
       }
     };
-    if (tc.post) { for (; rissued < NRBUF; ++rissued) issue_r(rissued); }
+    int issued = 0;  // main chunks issued so far; the post-multiplier prefetch follows the first ring fill
     for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
       const double* srcA; const double* srcB; int64_t ldA, ldB;
       if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }
@@ -344,6 +365,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
         if (lane < KT) bulk_g2s(dst + lane * LDS_T, srcA + (int64_t)(c * KT + lane) * ldA, NB * sizeof(double), &full[stage]);
         else bulk_g2s(dst + KT * LDS_T + (lane - KT) * LDS_T, srcB + (int64_t)(c * KT + lane - KT) * ldB, NB * sizeof(double), &full[stage]);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        if (++issued == NSTAGE && tc.post) { for (; rissued < NRBUF; ++rissued) issue_r(rissued); }
       }
     }
     if (tc.post) for (; rissued < NB / KT; ++rissued) issue_r(rissued);
