@@ -58,66 +58,65 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
   double logdet = 0.0;
 
   // ================= phase A: right-looking Cholesky over 32-wide sub-block columns =================
-  for (int jj = 0; jj < NSB; ++jj) {
+#pragma unroll 1
+  for (int jj = 0; jj < NSB; ++jj) {  // not unrolled: the straight-line sub-block code below is reused by all four iterations
     const int j0 = jj * SB;
     if (warp == 0) {
-      // ---- A1: potf2 + trtri of the 32x32 diagonal sub-block by one warp, lane r owns row r / column r.
-      // Rolled loops over shared memory (a fully unrolled register version is instruction-fetch bound).
+      // ---- A1: potf2 + trtri of the 32x32 diagonal sub-block by one warp, entirely in registers.
+      // This is the serial critical path of the whole block (7 warps wait), so it is written for latency:
+      //   potf2  right-looking, lane r owns row r (32 doubles); pivots / column entries broadcast by shuffles;
+      //          one rsqrt per pivot (no sqrt + divide), logs taken once per lane afterwards
+      //   trtri  column-oriented forward substitution, lane c owns column c of W = inv(L_dd); L(r,k) is a
+      //          broadcast shared-memory read, all updates of one step are independent FMAs
+      // Both are straight-line (fully unrolled, ~3.5k instructions, reused by the four sub-block iterations).
       double* D = S + j0 * LDS_T + j0;  // D(r,c) = D[c*LDS_T + r]
+      double a[SB];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) a[c] = D[c * LDS_T + lane];
       int bad = 0;
-      // left-looking (dot-product) form: only loads + FMAs inside the k loop, one store per column
+      double mydinv = 1.0;  // lane c ends up with 1 / L_cc
+#pragma unroll
       for (int c = 0; c < SB; ++c) {
-        double a0 = 0.0, a1 = 0.0;
-        int k = 0;
-        for (; k + 1 < c; k += 2) {
-          a0 = fma(D[k * LDS_T + lane], D[k * LDS_T + c], a0);              // L(lane,k) L(c,k)
-          a1 = fma(D[(k + 1) * LDS_T + lane], D[(k + 1) * LDS_T + c], a1);
-        }
-        if (k < c) a0 = fma(D[k * LDS_T + lane], D[k * LDS_T + c], a0);
-        const double v = D[c * LDS_T + lane] - (a0 + a1);                    // valid for lane >= c
-        double piv = __shfl_sync(FULL, v, c);
+        double piv = __shfl_sync(FULL, a[c], c);
         if (!(piv > 0.0)) {  // LAPACK dpotf2 rule: pivot <= 0 or NaN
           if (bad == 0) bad = j0 + c + 1;
           piv = 1.0;
         }
-        // one reciprocal square root instead of sqrt + divide + log on the serial critical path of the block
-        // (each is a long dependent instruction sequence); the logs are taken once per lane after the loop
         const double inv = rsqrt(piv);
-        const double l = piv * inv;
-        if (lane > c) D[c * LDS_T + lane] = v * inv;
-        else if (lane == c) { D[c * LDS_T + c] = l; dinv32[c] = inv; }
-        __syncwarp();
+        const double lrc = (lane == c) ? piv * inv : a[c] * inv;  // L(lane, c), valid for lane >= c
+        a[c] = lrc;
+        if (lane == c) mydinv = inv;
+#pragma unroll
+        for (int k = c + 1; k < SB; ++k) a[k] = fma(-lrc, __shfl_sync(FULL, lrc, k), a[k]);  // valid for lane >= k
       }
       if (bad != 0 && lane == 0 && bad_col == 0) bad_col = bad;
-      logdet += log(D[lane * LDS_T + lane]);  // lane c holds log L_cc; warp-reduced once at the end of the kernel
-      // L_dd straight to HBM (lower), zeros above the diagonal
-      for (int c = 0; c < SB; ++c) T[(j0 + lane) + (int64_t)(j0 + c) * npad] = (lane >= c) ? D[c * LDS_T + lane] : 0.0;
-      // W = inv(L_dd): lane c owns column c; W(r,c), r > c, is parked transposed at D(c,r) (strict upper part)
-      const double wcc = dinv32[lane];
-      for (int r = 1; r < SB; ++r) {
-        double s0 = 0.0, s1 = 0.0;
-        if (r > lane) {
-          s0 = D[lane * LDS_T + r] * wcc;  // L(r,c) W(c,c)
-          int k = lane + 1;
-          for (; k + 1 < r; k += 2) {
-            s0 = fma(D[k * LDS_T + r], D[k * LDS_T + lane], s0);
-            s1 = fma(D[(k + 1) * LDS_T + r], D[(k + 1) * LDS_T + lane], s1);
-          }
-          if (k < r) s0 = fma(D[k * LDS_T + r], D[k * LDS_T + lane], s0);
-          D[r * LDS_T + lane] = -(s0 + s1) * dinv32[r];
-        }
-        __syncwarp();
+      logdet -= log(mydinv);  // log L_cc = -log(1 / L_cc) of this lane's pivot; warp-reduced once at the end of the kernel
+      // L_dd: lower part back into D (read by the inverse below) and straight to HBM, zeros above the diagonal
+#pragma unroll
+      for (int c = 0; c < SB; ++c) {
+        const double v = (lane >= c) ? a[c] : 0.0;
+        D[c * LDS_T + lane] = v;
+        T[(j0 + lane) + (int64_t)(j0 + c) * npad] = v;
       }
-      // finalise: D becomes W_dd^T (upper incl. diagonal, zeros below); Dd[jj] gets W_dd column-major
+      dinv32[lane] = mydinv;
+      __syncwarp();
+      // W = inv(L_dd), column `lane`: solve L w = e_lane
+      double w[SB];
+#pragma unroll
+      for (int r = 0; r < SB; ++r) w[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < SB; ++k) {
+        w[k] *= dinv32[k];
+#pragma unroll
+        for (int r = k + 1; r < SB; ++r) w[r] = fma(-D[k * LDS_T + r], w[k], w[r]);  // L(r,k): broadcast read
+      }
+      __syncwarp();
+      // finalise: D becomes W_dd^T (upper incl. diagonal, exact zeros below); Dd[jj] gets W_dd column-major
       double* Dj = Dd + jj * SB * LDW;
+#pragma unroll
       for (int r = 0; r < SB; ++r) {
-        double wt;  // W^T(lane, r) = W(r, lane)
-        if (r > lane) wt = D[r * LDS_T + lane];
-        else if (r == lane) wt = wcc;
-        else wt = 0.0;
-        __syncwarp();
-        D[r * LDS_T + lane] = wt;
-        Dj[r + lane * LDW] = wt;  // W(r, lane)
+        D[r * LDS_T + lane] = w[r];   // W^T(lane, r) = W(r, lane)
+        Dj[r + lane * LDW] = w[r];    // W(r, lane)
       }
     }
     __syncthreads();
