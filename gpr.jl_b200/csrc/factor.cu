@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
   const int gp = g.list ? g.list[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, t = lane & 3;
+  const int warp_u = __shfl_sync(FULL, warp, 0);  // warp index through the uniform datapath
   const int j = g.step;
   const int64_t npad = g.npad;
   if (g.fail[gp] != 0) return;  // already failed (or non-finite theta): results are discarded by the host
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
 #pragma unroll 1
   for (int jj = 0; jj < NSB; ++jj) {  // not unrolled: the straight-line sub-block code below is reused by all four iterations
     const int j0 = jj * SB;
-    if (warp == 0) {
+    if (warp_u == 0) {  // provably warp-uniform branch: the shuffles below compile to plain SHFL (no collective wrappers)
       // ---- A1: potf2 + trtri of the 32x32 diagonal sub-block by one warp, entirely in registers.
       // This is the serial critical path of the whole block (7 warps wait), so it is written for latency:
       //   potf2  right-looking, lane r owns row r (32 doubles); pivots / column entries broadcast by shuffles;
