@@ -2,6 +2,7 @@
 // evaluation pipeline  assembly -> blocked Cholesky -> solves/mll -> inverse -> fused gradient.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -44,7 +45,7 @@ static void free_batch(gprb_batch* b) {
   if (b->list_host) cudaFreeHost(b->list_host);
   if (b->fail_host) cudaFreeHost(b->fail_host);
   if (b->stage_host) cudaFreeHost(b->stage_host);
-  for (int s = 0; s < 4; ++s) {
+  for (int s = 0; s < MAX_STREAMS; ++s) {
     if (b->stream[s]) cudaStreamDestroy(b->stream[s]);
     if (b->join[s]) cudaEventDestroy(b->join[s]);
   }
@@ -419,7 +420,8 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
       break;
     }
     b->nstreams = 4;
-    for (int s = 0; s < 4 && !rc; ++s) {
+    if (const char* ev = getenv("GPRB200_STREAMS")) b->nstreams = std::max(1, std::min(MAX_STREAMS, atoi(ev)));
+    for (int s = 0; s < MAX_STREAMS && !rc; ++s) {
       if ((e = cudaStreamCreateWithFlags(&b->stream[s], cudaStreamNonBlocking)) != cudaSuccess ||
           (e = cudaEventCreateWithFlags(&b->join[s], cudaEventDisableTiming)) != cudaSuccess)
         rc = cuda_fail(e, "stream/event create", __FILE__, __LINE__);

@@ -16,6 +16,7 @@ constexpr int LDS_T = NB + 4;  // padded smem row (doubles): (t*132 + g) mod 16 
 constexpr int MAX_D = 62;      // 13 * bodies <= 52 in the reference (src/CState.jl:20); (MAX_D + 2) * 128 doubles fit the
                                // 64 KB landing zone the gradient kernel reuses as its reduction buffer
 constexpr int MAX_JITTER = 10; // make_posdef! retries (GaussianProcesses 0.12.4)
+constexpr int MAX_STREAMS = 8; // the GPs of one call are split over up to this many streams (GPRB200_STREAMS, default 4)
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -89,10 +90,10 @@ struct gprb_batch {
   int32_t* fail_host = nullptr;   // pinned
   double* stage_host = nullptr;   // pinned staging for theta / results
   int64_t stage_doubles = 0;
-  cudaStream_t stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t stream[gprb::MAX_STREAMS] = {};
   int nstreams = 1;
   cudaEvent_t ev[8] = {};
-  cudaEvent_t join[4] = {};
+  cudaEvent_t join[gprb::MAX_STREAMS] = {};
   bool profiling = false;
   std::vector<uint8_t> state_ok;  // per GP: factor + alpha resident (last evaluation succeeded)
   std::vector<uint8_t> inv_ok;    // per GP: K^-1 resident in A (last evaluation was value+gradient)
@@ -156,6 +157,36 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// exp(x) for x <= 0, branch-free (the library exp carries range-check branches that keep the compiler from
+// interleaving neighbouring evaluations; the pairwise kernels evaluate 64 per thread).  Cody-Waite reduction with
+// k = rint(x log2 e), degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), 2^k applied as two exact
+// power-of-two factors so gradual underflow needs no special case.  <= 1 ulp in the normal range (tests/test_oracle
+// pins it against numpy through the K parity bound); x < -800 is clamped (exp underflows to 0), NaN propagates.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double xc = x < -800.0 ? -800.0 : x;
+  const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);
+  const double k = t - 6755399441055744.0;
+  const int ki = __double2loint(t);
+  double r = fma(k, -6.93147180369123816490e-01, xc);
+  r = fma(k, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;        // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);      // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);     // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);     // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);    // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);      // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);     // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);     // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);     // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);    // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);    // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k1 = ki >> 1, k2 = ki - k1;
+  return p * __hiloint2double((k1 + 1023) << 20, 0) * __hiloint2double((k2 + 1023) << 20, 0);
 }
 
 // D(8x8) += A(8x4, row) * B(4x8, col) in fp64 on the tensor pipe (SASS DMMA.8x8x4).

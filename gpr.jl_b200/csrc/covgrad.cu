@@ -8,6 +8,10 @@
 // The gradient kernel never materialises Q = alpha alpha' - K^-1 or dK/dtheta:
 //     g_noise = s_n^2 tr(Q),  g_ll_p = 1/2 w_p sum_ij Q_ij g(r_ij) (x_ip - x_jp)^2,  g_lsigma = sum_ij Q_ij K_f,ij
 // Per-tile partial sums are written to HBM and reduced in a fixed order by a second kernel (deterministic).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,20 +23,20 @@ constexpr double EPS_F64 = 2.220446049250313e-16;
 template <int KIND>
 __device__ __forceinline__ void kfun(double r2, double sf2, double& kf, double& gf) {
   if (KIND == GPRB_KERNEL_SE_ARD) {
-    kf = sf2 * exp(-0.5 * r2);
+    kf = sf2 * exp_nonpos(-0.5 * r2);
     gf = kf;
   } else if (KIND == GPRB_KERNEL_MAT12_ARD) {
     const double r = sqrt(r2);
-    kf = sf2 * exp(-r);
+    kf = sf2 * exp_nonpos(-r);
     gf = r > 0.0 ? kf / r : 0.0;
   } else if (KIND == GPRB_KERNEL_MAT32_ARD) {
     const double s = 1.7320508075688772 * sqrt(r2);
-    const double e = exp(-s);
+    const double e = exp_nonpos(-s);
     kf = sf2 * (1.0 + s) * e;
     gf = 3.0 * sf2 * e;
   } else {
     const double s = 2.23606797749979 * sqrt(r2);
-    const double e = exp(-s);
+    const double e = exp_nonpos(-s);
     kf = sf2 * (1.0 + s + 5.0 * r2 / 3.0) * e;
     gf = (5.0 / 3.0) * sf2 * (1.0 + s) * e;
   }
@@ -138,6 +142,148 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_assemble(AssembleArgs g) {
       }
       *reinterpret_cast<double2*>(A + r + (int64_t)c * g.npad) = make_double2(v[0], v[1]);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Covariance assembly with the cross term on the FP64 tensor pipe (default path).
+//   z_ip = sqrt(w_p) (x_ip - x_0p)         scaled inputs, centred at the dataset's first sample (constant input
+//                                          dimensions become exact zeros), built in shared memory per tile
+//   r2_ij = |z_i|^2 + |z_j|^2 - 2 z_i.z_j  the d-long contraction z_i.z_j runs as DMMA.8x8x4 tiles (SASS DMMA)
+// The expansion loses accuracy by ~ (d/4 + 2) eps (|z_i|^2 + |z_j|^2) in r2, i.e. half of that relative in K.
+// Parity with the reference's direct differences (1e-12 relative on K) is kept by a guard: pairs whose norm sum
+// exceeds GRAM_SMAX and whose K is not an underflow (r2 < GRAM_R2CUT) are recomputed with direct differences of the
+// raw inputs.  With trajectory data and sane length-scales the guard never fires (|z|^2 << 1); extreme
+// length-scales (config.json has l down to 1e-4) take the slow exact path per element.
+// One CTA (256 threads, 8 warps of 32 x 32 register tiles) = 128 rows x 64 columns of a lower tile; two CTAs per SM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GA_THREADS = 256;
+constexpr int GA_CW = 64;             // columns per CTA
+constexpr int GA_LDJ = GA_CW + 4;     // padded row of the column-input tile (conflict-free B fragments)
+constexpr double GRAM_SMAX = 16.0;    // (d/4 + 2) eps * 16 < 4e-14 for d <= 62
+constexpr double GRAM_R2CUT = 1500.0; // exp(-750) underflows to zero: pairs beyond it are exact zeros either way
+
+template <int KIND>
+__global__ void __launch_bounds__(GA_THREADS, 2) k_assemble_gram(AssembleArgs g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = g.d, dpad = (d + 3) & ~3;
+  double* Zi = reinterpret_cast<double*>(smem_raw);   // [dpad][LDS_T]  row-input tile, one padded row per dimension
+  double* Zj = Zi + dpad * LDS_T;                      // [dpad][GA_LDJ] column-input tile
+  const int zreg = max(dpad * (LDS_T + GA_LDJ), GA_CW * LDS_T);  // the input tiles' space later holds the cross-term tile
+  double* w = Zi + zreg;                               // [MAX_D + 2]  w_p
+  double* sw = w + MAX_D + 2;                          // [MAX_D + 2]  sqrt(w_p)
+  double* x0 = sw + MAX_D + 2;                         // [MAX_D + 2]  centre: first sample of the dataset
+  double* ni = x0 + MAX_D + 2;                         // [NB]     |z_i|^2
+  double* nj = ni + NB;                                // [GA_CW]  |z_j|^2
+  uint64_t* bar = reinterpret_cast<uint64_t*>(nj + GA_CW);
+  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
+  int ti, tj;
+  lower_tile(tile, ti, tj);
+  const double* th = g.theta + (int64_t)gp * (d + 2);
+  const double* Xt = g.Xt[gp];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = tj * NB + half * GA_CW;  // first global column of this CTA
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncthreads();
+  if (tid == 0) mbar_expect_tx(bar, (uint32_t)(d * (NB + GA_CW) * sizeof(double)));
+  __syncthreads();
+  for (int k = tid; k < 2 * d; k += GA_THREADS) {
+    if (k < d) bulk_g2s(Zi + k * LDS_T, Xt + (int64_t)k * g.npad + (int64_t)ti * NB, NB * sizeof(double), bar);
+    else bulk_g2s(Zj + (k - d) * GA_LDJ, Xt + (int64_t)(k - d) * g.npad + c0, GA_CW * sizeof(double), bar);
+  }
+  if (tid < d) {
+    const double wp = exp(-2.0 * th[1 + tid]);  // SEArd stores il2 = exp(-2 ll)
+    w[tid] = wp;
+    sw[tid] = sqrt(wp);
+    x0[tid] = Xt[(int64_t)tid * g.npad];
+  }
+  for (int k = d * LDS_T + tid; k < dpad * LDS_T; k += GA_THREADS) Zi[k] = 0.0;  // zero rows d .. dpad-1
+  for (int k = d * GA_LDJ + tid; k < dpad * GA_LDJ; k += GA_THREADS) Zj[k] = 0.0;
+  const double sf2 = exp(2.0 * th[d + 1]);
+  const double diag_add = exp(2.0 * th[0]) + EPS_F64 + g.jitter[gp];
+  mbar_wait(bar, 0);
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) {  // info -2: non-finite theta / kernel scale (also resets the flag)
+    bool ok = isfinite(sf2) && isfinite(diag_add);
+    for (int p = 0; p < d + 2; ++p) ok = ok && isfinite(th[p]);
+    for (int p = 0; p < d; ++p) ok = ok && isfinite(w[p]);
+    g.fail[gp] = ok ? 0 : -2;
+  }
+  // scale + centre in place, then the squared norms (thread r: row r, threads < 64: column r as well)
+  for (int k = tid; k < d * NB; k += GA_THREADS) {
+    const int p = k >> 7, r = k & (NB - 1);
+    Zi[p * LDS_T + r] = sw[p] * (Zi[p * LDS_T + r] - x0[p]);
+  }
+  for (int k = tid; k < d * GA_CW; k += GA_THREADS) {
+    const int p = k >> 6, r = k & (GA_CW - 1);
+    Zj[p * GA_LDJ + r] = sw[p] * (Zj[p * GA_LDJ + r] - x0[p]);
+  }
+  __syncthreads();
+  if (tid < NB) {
+    double s = 0.0;
+    for (int p = 0; p < d; ++p) { const double z = Zi[p * LDS_T + tid]; s = fma(z, z, s); }
+    ni[tid] = s;
+  } else if (tid < NB + GA_CW) {
+    double q = 0.0;
+    for (int p = 0; p < d; ++p) { const double z = Zj[p * GA_LDJ + tid - NB]; q = fma(z, z, q); }
+    nj[tid - NB] = q;
+  }
+  // cross term z_i . z_j on the tensor pipe
+  const int wm = warp & 3, wn = warp >> 2;
+  const int gq = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni_ = 0; ni_ < 4; ++ni_) acc[mi][ni_][0] = acc[mi][ni_][1] = 0.0;
+  for (int k4 = 0; k4 < dpad / 4; ++k4) {
+    double a[4], b[4];
+    const double* ap = Zi + (k4 * 4 + t) * LDS_T + wm * 32 + gq;
+    const double* bp = Zj + (k4 * 4 + t) * GA_LDJ + wn * 32 + gq;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = ap[mi * 8];
+#pragma unroll
+    for (int ni_ = 0; ni_ < 4; ++ni_) b[ni_] = bp[ni_ * 8];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni_ = 0; ni_ < 4; ++ni_) dmma884(acc[mi][ni_][0], acc[mi][ni_][1], a[mi], b[ni_]);
+  }
+  __syncthreads();  // norms visible; every warp is done with the input tiles: their space becomes the cross-term tile
+  double* Cs = Zi;  // [GA_CW][LDS_T] column-major z_i.z_j
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni_ = 0; ni_ < 4; ++ni_) {
+      const int rl = wm * 32 + mi * 8 + gq, cl = wn * 32 + ni_ * 8 + 2 * t;
+      Cs[cl * LDS_T + rl] = acc[mi][ni_][0];
+      Cs[(cl + 1) * LDS_T + rl] = acc[mi][ni_][1];
+    }
+  __syncthreads();
+  // epilogue, rolled (a fully unrolled register epilogue is instruction-fetch bound): thread = (row, 32-column half);
+  // consecutive lanes write consecutive rows of one column (full 128 B lines)
+  double* A = g.A + (int64_t)gp * g.mat_stride;
+  const int n = g.n;
+  const int rl = tid & (NB - 1), rr = ti * NB + rl, cbeg = (tid >> 7) * (GA_CW / 2);
+  const double nr = ni[rl];
+#pragma unroll 8
+  for (int cl = cbeg; cl < cbeg + GA_CW / 2; ++cl) {
+    const int c = c0 + cl;
+    const double ssum = nr + nj[cl];
+    double r2 = fmax(ssum - 2.0 * Cs[cl * LDS_T + rl], 0.0);
+    if (ssum > GRAM_SMAX && r2 < GRAM_R2CUT && rr < n && c < n) {  // exact path: direct differences of the raw inputs
+      r2 = 0.0;
+      for (int p = 0; p < d; ++p) {
+        const double df = Xt[(int64_t)p * g.npad + rr] - Xt[(int64_t)p * g.npad + c];
+        r2 = fma(w[p], df * df, r2);
+      }
+    }
+    double kf, gf;
+    kfun<KIND>(r2, sf2, kf, gf);
+    if (rr == c) kf = sf2 + diag_add;            // r2 is exactly zero on the diagonal
+    if (rr >= n || c >= n) kf = (rr == c) ? 1.0 : 0.0;
+    A[rr + (int64_t)c * g.npad] = kf;
   }
 }
 
@@ -355,14 +501,33 @@ static int set_smem(K kernel, size_t bytes) {
 
 int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream) {
   if (count <= 0) return 0;
-  const size_t smem = pw_smem(a.d, false);
-  dim3 grid(a.J * (a.J + 1) / 2, count);
+  // GPRB200_ASSEMBLY=direct selects the all-direct-difference kernel (A/B comparisons, tests); default is the DMMA path
+  static const bool direct = [] { const char* e = getenv("GPRB200_ASSEMBLY"); return e && e[0] == 'd'; }();
   int rc = 0;
-  switch (a.kind) {
-    case GPRB_KERNEL_SE_ARD: rc = set_smem(k_assemble<0>, smem); if (!rc) k_assemble<0><<<grid, PW_THREADS, smem, stream>>>(a); break;
-    case GPRB_KERNEL_MAT12_ARD: rc = set_smem(k_assemble<1>, smem); if (!rc) k_assemble<1><<<grid, PW_THREADS, smem, stream>>>(a); break;
-    case GPRB_KERNEL_MAT32_ARD: rc = set_smem(k_assemble<2>, smem); if (!rc) k_assemble<2><<<grid, PW_THREADS, smem, stream>>>(a); break;
-    default: rc = set_smem(k_assemble<3>, smem); if (!rc) k_assemble<3><<<grid, PW_THREADS, smem, stream>>>(a); break;
+  if (!direct) {
+    const int dpad = (a.d + 3) & ~3;
+    const size_t zreg = std::max((size_t)dpad * (LDS_T + GA_LDJ), (size_t)GA_CW * LDS_T);  // input tiles, later the cross-term tile
+    const size_t smem = (zreg + 3 * (MAX_D + 2) + NB + GA_CW) * sizeof(double) + 16;
+    dim3 grid(a.J * (a.J + 1) / 2 * (NB / GA_CW), count);
+#define GPRB_GA_CASE(K)                                 \
+  rc = set_smem(k_assemble_gram<K>, smem);              \
+  if (!rc) k_assemble_gram<K><<<grid, GA_THREADS, smem, stream>>>(a);
+    switch (a.kind) {
+      case GPRB_KERNEL_SE_ARD: GPRB_GA_CASE(0) break;
+      case GPRB_KERNEL_MAT12_ARD: GPRB_GA_CASE(1) break;
+      case GPRB_KERNEL_MAT32_ARD: GPRB_GA_CASE(2) break;
+      default: GPRB_GA_CASE(3) break;
+    }
+#undef GPRB_GA_CASE
+  } else {
+    const size_t smem = pw_smem(a.d, false);
+    dim3 grid(a.J * (a.J + 1) / 2, count);
+    switch (a.kind) {
+      case GPRB_KERNEL_SE_ARD: rc = set_smem(k_assemble<0>, smem); if (!rc) k_assemble<0><<<grid, PW_THREADS, smem, stream>>>(a); break;
+      case GPRB_KERNEL_MAT12_ARD: rc = set_smem(k_assemble<1>, smem); if (!rc) k_assemble<1><<<grid, PW_THREADS, smem, stream>>>(a); break;
+      case GPRB_KERNEL_MAT32_ARD: rc = set_smem(k_assemble<2>, smem); if (!rc) k_assemble<2><<<grid, PW_THREADS, smem, stream>>>(a); break;
+      default: rc = set_smem(k_assemble<3>, smem); if (!rc) k_assemble<3><<<grid, PW_THREADS, smem, stream>>>(a); break;
+    }
   }
   if (rc) return rc;
   cudaError_t e = cudaGetLastError();
