@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 N_TRAIN, TRIALS, SYSTEM = 2000, 100, "CP"
 METRIC = "batched fp64 logML+gradient evals/sec (n=2000)"
+WORKLOAD_NAMES = {"P1": "P1 simple pendulum", "P2": "P2 double pendulum", "CP": "CP cartpole noise experiment", "FB": "FB fourbar"}
 
 
 def flops_eval(n, d):  # minimal algorithm, value+gradient
@@ -129,6 +130,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--trials", type=int, default=TRIALS, help="trial datasets per GPU (default: the full 100)")
     ap.add_argument("--n", type=int, default=N_TRAIN)
+    ap.add_argument("--system", default=SYSTEM, choices=["P1", "P2", "CP", "FB"],
+                    help="BASELINE config family (default CP, the one the metric is quoted on); FB = d=52, 12 GPs per trial")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-predict", action="store_true")
     args = ap.parse_args()
@@ -150,7 +153,8 @@ def main():
     from gpr_jl_b200 import data
 
     n, T = args.n, args.trials
-    trials = data.make_config(SYSTEM, trials=T, n=n, first_trial=rank * T)
+    trials = data.make_config(args.system, trials=T, n=n, first_trial=rank * T)
+    G_out = trials[0]["Y"].shape[0]
     d = trials[0]["X"].shape[0]
     gps = []
     for tr in trials:
@@ -242,7 +246,7 @@ def main():
     gemm_flops = float(B) * n ** 3  # potrf n^3/3 + inverse-from-factor 2n^3/3 (algorithmic, un-padded)
     achieved = gemm_flops / (st["gemm"] * 1e-3) / 1e12 if st["gemm"] > 0 else 0.0
     traffic, traffic_src = None, None
-    if n == N_TRAIN and T == TRIALS:  # ncu dram__bytes_read+write per launch, captured at exactly this configuration
+    if n == N_TRAIN and T == TRIALS and args.system == SYSTEM:  # ncu dram__bytes_read+write per launch, captured at exactly this configuration
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
             traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_traffic.json (tools/traffic.sh: ncu dram bytes, mean of the 47 launches of one evaluation)"
@@ -259,7 +263,7 @@ def main():
     pred = None
     if not args.no_predict:
         m = 100
-        Xt = data.make_trial(SYSTEM, 8, seed=99, n_test=m)["Xtest"]
+        Xt = data.make_trial(args.system, 8, seed=99, n_test=m)["Xtest"]
         batch.predict_y(Xt, var=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -278,8 +282,9 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"CP cartpole noise experiment, n={n}, d={d}, G=4 GPs/trial, {T} trials (B={B} GPs per GPU)",
-                       "evals_per_step": world * B, "theta": "config.json CP_MAX2048 + 0.1*N(0,I), fresh per step",
+            "config": {"workload": f"{WORKLOAD_NAMES[args.system]}, n={n}, d={d}, G={G_out} GPs/trial, {T} trials (B={B} GPs per GPU)",
+                       "evals_per_step": world * B,
+                       "theta": ("config.json CP_MAX2048" if args.system == "CP" else "theta_0 of the config (data.CONFIGS)") + " + 0.1*N(0,I), fresh per step",
                        "l2": f"working set {2 * B * batch.n * batch.n * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "info_ok": info_ok, "parallelism": f"trial-sharded x{world}, per-step NCCL all-gather of results"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -298,6 +298,35 @@ def test_optimize_matches_scalar_oracle(gprb):
     assert np.all(np.isfinite(mu)) and np.all(var > 0)
 
 
+def test_trial_results_reproduced_within_tolerance(gprb):
+    """north_star: >= 95 % of trial results reproduced within tolerance.  32 GPs (8 CP trials x 4 outputs, n = 80)
+    optimised in lock-step for 8 L-BFGS iterations vs the scalar Optim restatement driving the CPU oracle, one GP at a
+    time; a trial counts as reproduced when every output's final mll agrees to 1e-6 relative (line-search decisions at
+    ties may legitimately bifurcate) and the hyper-parameters to 1e-4."""
+    from gpr_jl_b200 import data
+    trials = [data.make_trial("CP", 80, seed=300 + t) for t in range(8)]
+    thetas = []
+    for tr in trials:
+        th = data.theta0("CP", tr["X"])
+        thetas.append(np.tile(th, (4, 1)))
+    batch = build_batch(gprb, trials, thetas)
+    res = batch.optimize(gprb.LBFGS(linesearch=gprb.BackTracking(order=2)), gprb.Options(iterations=8))
+    ok_trials = 0
+    for t, tr in enumerate(trials):
+        X = np.ascontiguousarray(tr["X"].T)
+        good = True
+        for k in range(4):
+            f = lambda th_: -go.eval_mll(X, tr["Y"][k], th_, with_grad=False)["mll"]
+            def fg(th_):
+                r = go.eval_mll(X, tr["Y"][k], th_)
+                return (-r["mll"], -r["grad"]) if r["info"] >= 0 else (np.inf, np.full(th_.size, np.nan))
+            o = lbfgs(f, fg, thetas[t][k], LBFGSOptions(iterations=8))
+            r = res[4 * t + k]
+            good = good and abs(r["minimum"] - o.f) <= 1e-6 * abs(o.f) and rel(r["minimizer"], o.x) <= 1e-4
+        ok_trials += good
+    assert ok_trials >= 0.95 * len(trials), ok_trials
+
+
 def test_reference_call_sequence_single_gp(gprb):
     """The literal per-GP sequence of CPnoise.jl:38-41 + predictdynamics.jl:13."""
     from gpr_jl_b200 import data
