@@ -297,16 +297,19 @@ constexpr int GRAD_CW = NB / GRAD_PARTS_PER_TILE;  // 32
 constexpr int GRAD_THREADS = 128;
 static_assert(GRAD_CW == 32, "thread mapping below assumes 32-column blocks");
 
-template <int KIND>
+constexpr int GRAD_DH = 32;  // input dimensions resident at a time: d > 32 (FB: d = 52) streams its input tiles in two passes
+                             // so that the CTA stays at ~105 KB of smem and two CTAs fit an SM for every d
+
+template <int KIND, bool MULTI>  // MULTI = false: d <= GRAD_DH, one resident pass (the common case compiles without the pass logic)
 __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
-  constexpr int CW = GRAD_CW, NT = GRAD_THREADS, NQ = NB / CW;
+  constexpr int CW = GRAD_CW, NT = GRAD_THREADS, NQ = NB / CW, DH = MULTI ? GRAD_DH : MAX_D + 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int d = g.d;
+  const int d = g.d, dh = min(d, DH), npass = MULTI ? (d + DH - 1) / DH : 1;
   double* Ki = reinterpret_cast<double*>(smem_raw);  // [CW][NB] K^-1 block, column-major; reused as `red` afterwards
   double* Kb = Ki + CW * NB;                          // [CW][NB] K block (SEArd only)
-  double* Xi = Kb + CW * NB;                          // [d][NB]
-  double* Xj = Xi + d * NB;                           // [d][CW]
-  double* w = Xj + d * CW;                            // [MAX_D]
+  double* Xi = Kb + CW * NB;                          // [dh][NB]  input tile of the current pass
+  double* Xj = Xi + dh * NB;                          // [dh][CW]
+  double* w = Xj + dh * CW;                           // [MAX_D]
   uint64_t* bar = reinterpret_cast<uint64_t*>(w + MAX_D);
   double* red = Ki;                                   // [(d + 2)][NT] <= 2 * CW * NB doubles for d <= 62
   const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
@@ -324,15 +327,31 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
   else { ldk = g.npad; Kinv = g.A + (int64_t)gp * g.mat_stride + (int64_t)tj * NB + ((int64_t)ti * NB + cbase) * ldk; }
   if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
-  if (threadIdx.x == 0)
-    mbar_expect_tx(bar, (uint32_t)((d * (NB + CW) + (REUSE_K ? 2 : 1) * CW * NB) * sizeof(double)));
-  __syncthreads();
-  // 32 + 32 matrix columns, d + d input rows: one bulk copy each
-  for (int k = threadIdx.x; k < 2 * CW + 2 * d; k += NT) {
+  // Input tiles of pass q (dimensions q*DH ..): one bulk copy per dimension and tile.  `cur` = resident pass.
+  uint32_t parity = 0;
+  int cur = 0;
+  auto issue_x = [&](int q, uint32_t extra_bytes) {
+    const int p0 = q * DH, pc = min(DH, d - p0);
+    if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(pc * (NB + CW) * sizeof(double)) + extra_bytes);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * pc; k += NT) {
+      if (k < pc) bulk_g2s(Xi + k * NB, Xt + (int64_t)(p0 + k) * g.npad + (int64_t)ti * NB, NB * sizeof(double), bar);
+      else bulk_g2s(Xj + (k - pc) * CW, Xt + (int64_t)(p0 + k - pc) * g.npad + (int64_t)tj * NB + cbase, CW * sizeof(double), bar);
+    }
+  };
+  auto need_pass = [&](int q) {  // make pass q resident (no-op when it already is)
+    if (!MULTI || q == cur) return;
+    __syncthreads();  // everyone is done reading the resident tiles
+    issue_x(q, 0);
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    cur = q;
+  };
+  // first batch: 32 + 32 matrix columns and the input tiles of pass 0, all in flight at once
+  issue_x(0, (uint32_t)((REUSE_K ? 2 : 1) * CW * NB * sizeof(double)));
+  for (int k = threadIdx.x; k < 2 * CW; k += NT) {
     if (k < CW) bulk_g2s(Ki + k * NB, Kinv + (int64_t)k * ldk, NB * sizeof(double), bar);
-    else if (k < 2 * CW) { if (REUSE_K) bulk_g2s(Kb + (k - CW) * NB, Kt + (int64_t)(k - CW) * g.npad, NB * sizeof(double), bar); }
-    else if (k < 2 * CW + d) bulk_g2s(Xi + (k - 2 * CW) * NB, Xt + (int64_t)(k - 2 * CW) * g.npad + (int64_t)ti * NB, NB * sizeof(double), bar);
-    else bulk_g2s(Xj + (k - 2 * CW - d) * CW, Xt + (int64_t)(k - 2 * CW - d) * g.npad + (int64_t)tj * NB + cbase, CW * sizeof(double), bar);
+    else if (REUSE_K) bulk_g2s(Kb + (k - CW) * NB, Kt + (int64_t)(k - CW) * g.npad, NB * sizeof(double), bar);
   }
   if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
   const double sf2 = exp(2.0 * th[d + 1]);
@@ -344,7 +363,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
   for (int a = 0; a < 8; ++a) ar[a] = alpha[ti * NB + loc8(a, tx)];
 #pragma unroll
   for (int b = 0; b < 4; ++b) ac[b] = alpha[tj * NB + cbase + 16 * (b >> 1) + 2 * ty + (b & 1)];
-  mbar_wait(bar, 0);
+  mbar_wait(bar, parity);
+  parity ^= 1;
   __syncthreads();  // w visible
   double m[8][4];
   if (!REUSE_K) {  // Matern needs r itself: distances from the staged inputs (m holds r2 for now)
@@ -352,26 +372,30 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
     for (int a = 0; a < 8; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) m[a][b] = 0.0;
-    for (int p = 0; p < d; ++p) {
-      double xr[8], xc[4];
+    for (int q = 0; q < npass; ++q) {
+      need_pass(q);
+      const int p0 = q * DH, pc = min(DH, d - p0);
+      for (int p = 0; p < pc; ++p) {
+        double xr[8], xc[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
-        xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
-      }
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + 16 * cb + 2 * ty);
-        xc[2 * cb] = u.x; xc[2 * cb + 1] = u.y;
-      }
-      const double wp = w[p];
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const double df = xr[a] - xc[b];
-          m[a][b] = fma(wp, df * df, m[a][b]);
+        for (int a = 0; a < 4; ++a) {
+          const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
+          xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
         }
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + 16 * cb + 2 * ty);
+          xc[2 * cb] = u.x; xc[2 * cb + 1] = u.y;
+        }
+        const double wp = w[p0 + p];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const double df = xr[a] - xc[b];
+            m[a][b] = fma(wp, df * df, m[a][b]);
+          }
+      }
     }
   }
   // phase 1: m_ij = (alpha_i alpha_j - Kinv_ij) g(r_ij).  SEArd: dK/dll_p = K_f w_p Delta_p^2 and K_f,ij (i != j) is
@@ -405,29 +429,35 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
     }
   }
   __syncthreads();  // every thread is done with the landed blocks: the space becomes `red`
-  // phase 2 (FP64 pipe): per-dimension weighted sums; one scalar per (p, thread) parked in smem
-  for (int p = 0; p < d; ++p) {
-    double xr[8], xc[4];
+  // phase 2 (FP64 pipe): per-dimension weighted sums; one scalar per (p, thread) parked in smem.  Passes start with
+  // the resident one (the last pass after a Matern distance sweep, pass 0 otherwise).
+  for (int qq = 0; qq < npass; ++qq) {
+    const int q = (cur + qq) % npass;
+    need_pass(q);
+    const int p0 = q * DH, pc = min(DH, d - p0);
+    for (int p = 0; p < pc; ++p) {
+      double xr[8], xc[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
-      xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
-    }
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + 16 * cb + 2 * ty);
-      xc[2 * cb] = u.x; xc[2 * cb + 1] = u.y;
-    }
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int a = 0; a < 8; a += 2)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const double d0 = xr[a] - xc[b], d1 = xr[a + 1] - xc[b];
-        s0 = fma(m[a][b], d0 * d0, s0);
-        s1 = fma(m[a + 1][b], d1 * d1, s1);
+      for (int a = 0; a < 4; ++a) {
+        const double2 v = *reinterpret_cast<const double2*>(Xi + p * NB + 32 * a + 2 * tx);
+        xr[2 * a] = v.x; xr[2 * a + 1] = v.y;
       }
-    red[p * NT + threadIdx.x] = s0 + s1;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + 16 * cb + 2 * ty);
+        xc[2 * cb] = u.x; xc[2 * cb + 1] = u.y;
+      }
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 8; a += 2)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double d0 = xr[a] - xc[b], d1 = xr[a + 1] - xc[b];
+          s0 = fma(m[a][b], d0 * d0, s0);
+          s1 = fma(m[a + 1][b], d1 * d1, s1);
+        }
+      red[(p0 + p) * NT + threadIdx.x] = s0 + s1;
+    }
   }
   red[d * NT + threadIdx.x] = s_sig;
   red[(d + 1) * NT + threadIdx.x] = s_tr;
@@ -488,7 +518,7 @@ __global__ void k_add_jitter(const double* theta, double* jitter, const int32_t*
 }
 
 static size_t pw_smem(int d, bool grad) {
-  size_t doubles = grad ? (size_t)2 * GRAD_CW * NB + (size_t)d * (NB + GRAD_CW) + MAX_D : (size_t)2 * d * NB + MAX_D;
+  size_t doubles = grad ? (size_t)2 * GRAD_CW * NB + (size_t)std::min(d, GRAD_DH) * (NB + GRAD_CW) + MAX_D : (size_t)2 * d * NB + MAX_D;
   return doubles * sizeof(double) + 16;
 }
 
@@ -541,8 +571,13 @@ int launch_grad(const GradArgs& a, int count, cudaStream_t stream) {
   dim3 grid(a.J * (a.J + 1) / 2 * (NB / GRAD_CW), count);
   int rc = 0;
 #define GPRB_GRAD_CASE(K)                                             \
-  rc = set_smem(k_grad_tiles<K>, smem);                               \
-  if (!rc) k_grad_tiles<K><<<grid, GRAD_THREADS, smem, stream>>>(a);
+  if (a.d <= GRAD_DH) {                                               \
+    rc = set_smem(k_grad_tiles<K, false>, smem);                      \
+    if (!rc) k_grad_tiles<K, false><<<grid, GRAD_THREADS, smem, stream>>>(a); \
+  } else {                                                            \
+    rc = set_smem(k_grad_tiles<K, true>, smem);                       \
+    if (!rc) k_grad_tiles<K, true><<<grid, GRAD_THREADS, smem, stream>>>(a);  \
+  }
   switch (a.kind) {
     case GPRB_KERNEL_SE_ARD: GPRB_GRAD_CASE(0) break;
     case GPRB_KERNEL_MAT12_ARD: GPRB_GRAD_CASE(1) break;

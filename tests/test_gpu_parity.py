@@ -107,13 +107,13 @@ def test_golden_vectors(gprb):
         np.testing.assert_allclose(var, z[f"{nm}/var"], rtol=ptol, atol=1e-13)
 
 
-@pytest.mark.parametrize("kind", ["mat12", "mat32", "mat52"])
-def test_matern_kernels(gprb, kind):
+@pytest.mark.parametrize("kind,system", [("mat12", "P2"), ("mat32", "P2"), ("mat52", "P2"), ("mat32", "FB")])
+def test_matern_kernels(gprb, kind, system):
     from gpr_jl_b200 import data
-    tr = data.make_trial("P2", 200, seed=5)
-    th = data.theta0("P2", tr["X"])
+    tr = data.make_trial(system, 200, seed=5)  # FB: d = 52 streams the gradient's input tiles in two passes
+    th = data.theta0(system, tr["X"])
     th[1:-1] -= 1.0
-    thetas = [np.tile(th, (6, 1))]
+    thetas = [np.tile(th, (tr["Y"].shape[0], 1))]
     batch = build_batch(gprb, [tr], thetas, kind=kind)
     mll, grad, info = batch.eval()
     for b, r in enumerate(oracle_all([tr], thetas, kind=kind)):
