@@ -70,6 +70,32 @@ def test_eval_parity_well_conditioned(gprb, system, n):
     assert g2 is None and np.array_equal(mll, mll2)
 
 
+@pytest.mark.parametrize("n,d", [(2, 13), (4, 26), (8, 3), (16, 2), (50, 5), (129, 4)])
+def test_tiny_n_and_minimal_coordinate_d(gprb, n, d):
+    """The reference sweeps n = 2, 4, 8 ... (examples/noise.jl:64, hyperparameter.jl:50) and its minimal-coordinate
+    experiments use d = 2..6 (examples/minimal_coordinates/*); both go through the same boundary."""
+    rng = np.random.default_rng(1000 * n + d)
+    X = np.asfortranarray(rng.standard_normal((d, n)))
+    Y = np.stack([np.sin(X[0]) + 0.05 * rng.standard_normal(n), X[d - 1] ** 2])
+    th = np.concatenate([[-1.0], np.log(np.full(d, 1.5)), [0.3]])
+    tr = {"X": X, "Y": Y}
+    thetas = [np.tile(th, (2, 1)) + 0.05 * rng.standard_normal((2, d + 2))]
+    batch = build_batch(gprb, [tr], thetas)
+    mll, grad, info = batch.eval(grad=True)
+    Xs = np.asfortranarray(rng.standard_normal((d, 3)))
+    mu, var = batch.predict_y(Xs)
+    for b, r in enumerate(oracle_all([tr], thetas)):
+        assert info[b] == 0
+        assert rel(batch.K(b), r["state"]["K"]) <= 1e-12
+        assert abs(mll[b] - r["mll"]) <= 1e-8 * max(abs(r["mll"]), 1.0)
+        assert rel(grad[b], r["grad"]) <= 1e-8
+        m_o, v_o = go.predict(np.ascontiguousarray(X.T), thetas[0][b], r["state"], np.ascontiguousarray(Xs.T))
+        assert rel(mu[b], m_o) <= 1e-9
+        np.testing.assert_allclose(var[b], v_o, rtol=1e-9, atol=1e-13)
+    res = batch.optimize(gprb.LBFGS(linesearch=gprb.BackTracking(order=2)), gprb.Options(iterations=3))
+    assert all(np.isfinite(r["minimum"]) for r in res)
+
+
 def test_eval_parity_config_thetas_conditioning_aware(gprb):
     """theta_0 from the reference's config.json (s_f ~ 300-450, cond(K) ~ 1e8-1e10)."""
     from gpr_jl_b200 import data
