@@ -85,16 +85,16 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
       std::vector<unsigned long long> h(tl_n);
       cudaStreamSynchronize(st);
       cudaMemcpy(h.data(), tl_dev, sizeof(unsigned long long) * tl_n, cudaMemcpyDeviceToHost);
-      double ph[6] = {0, 0, 0, 0, 0, 0}, tot = 0; size_t cnt = 0;
+      double ph[6] = {0, 0, 0, 0, 0, 0}, tot = 0, waitc = 0; size_t cnt = 0;
       for (size_t k = 0; k < tl_n; k += 8) {
         const unsigned long long* t = &h[k];
         if (!t[0] || !t[6]) continue;
         unsigned long long prev = t[0];
         for (int q = 1; q <= 6; ++q) { unsigned long long cur = t[q] ? t[q] : prev; ph[q - 1] += (double)(cur - prev); prev = cur; }
-        tot += (double)(t[6] - t[0]); ++cnt;
+        tot += (double)(t[6] - t[0]); waitc += (double)t[7]; ++cnt;
       }
-      if (cnt) fprintf(stderr, "TL mode %d step %2d tiles %6zu  fill %6.2f main %7.2f cin %6.2f park %6.2f post %6.2f store %6.2f  total %7.2f us\n",
-                       a.mode, a.step, cnt, ph[0] / cnt / 1e3, ph[1] / cnt / 1e3, ph[2] / cnt / 1e3, ph[3] / cnt / 1e3, ph[4] / cnt / 1e3, ph[5] / cnt / 1e3, tot / cnt / 1e3);
+      if (cnt) fprintf(stderr, "TL mode %d step %2d tiles %6zu  fill %6.2f main %7.2f cin %6.2f park %6.2f post %6.2f store %6.2f  total %7.2f us  (operand wait in main %6.2f us)\n",
+                       a.mode, a.step, cnt, ph[0] / cnt / 1e3, ph[1] / cnt / 1e3, ph[2] / cnt / 1e3, ph[3] / cnt / 1e3, ph[4] / cnt / 1e3, ph[5] / cnt / 1e3, tot / cnt / 1e3, waitc / cnt / 1965.0);
     }
     return r;
 #else

@@ -177,6 +177,9 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   // multiply structural zeros (or compute the unused upper half) are skipped through compile-time specialised
   // chunk bodies (no per-DMMA predicates); with the {wn, 3-wn} / {wm 0, 1} warp pairing every SMSP keeps 9/16 of
   // the work of those chunks.  Ragged tiles (last block row) select the row-limited body for their mi_valid slabs.
+#ifdef GPRB_TIMELINE
+  long long tl_wait = 0;  // cycles this warp spent waiting for operand chunks in the main loop
+#endif
   int npred = 0;
   if (g.mode == GEMM_LAUUM) npred = min(nchunks, NB / KT);
   else if (!RAGGED && g.mode == GEMM_CHOL_DIAG) npred = nchunks;
@@ -186,7 +189,13 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   {
     int stage = 0; uint32_t phase = 0;
     for (int c = 0; c < nchunks; ++c) {
+#ifdef GPRB_TIMELINE
+      const long long w0 = clock64();
       mbar_wait(&full[stage], phase);
+      tl_wait += clock64() - w0;
+#else
+      mbar_wait(&full[stage], phase);
+#endif
       if (c == 0) GPRB_TL(1);
       const double* As = stages + stage * STAGE_DOUBLES;
       int sel = sel_plain;
@@ -205,6 +214,9 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   }
 
   GPRB_TL(2);
+#ifdef GPRB_TIMELINE
+  if (g.tl && threadIdx.x == 0) g.tl[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = (unsigned long long)tl_wait;
+#endif
   GPRB_TL(3);
   double* Cout = g.Cout + (int64_t)gp * g.mat_stride;
   if (tc.post == 0) {
