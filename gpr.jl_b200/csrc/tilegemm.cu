@@ -3,9 +3,14 @@
 //
 // One CTA = one 128x128 output tile of one GP:
 //     acc = sum_{k-blocks} Aop[i-rows, k] * Bop[j-rows, k]^T          (both operands column-major, ld = npad)
-// Warp-specialised: warp 8 is the producer (1 KB bulk copies through the TMA engine, one operand
-// column each, completion counted on mbarriers), warps 0-7 are DMMA consumers with 64x32 register
-// tiles (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, the native fp64 tensor shape on sm_100a).
+// Warp-specialised, three warpgroups: warps 0-7 are DMMA consumers with 64x32 register tiles
+// (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, the native fp64 tensor shape on sm_100a); warp 8 is the producer
+// (1 KB bulk copies through the TMA engine, one operand column each, completion counted on mbarriers); warps
+// 9-11 only exist to complete its warpgroup.  Register reallocation (setmaxnreg): the CTA launches with 168
+// registers per thread, the producer warpgroup shrinks to 40 and the two consumer warpgroups grow to 232.  With
+// the plain 168-register cap (nine warps = three on one SMSP) the compiler streams the A fragments through a
+// single register pair and the LDS latency is exposed to the DMMA pipe (0.90 of its rate in the k-loop); with
+// 232 registers the fragments are double-buffered a whole k4-step ahead.
 // Padded smem rows (132 doubles) make every fragment load bank-conflict free.
 //
 // Modes (tile coordinates and k-range derive from `mode`, `step` and blockIdx.x):
@@ -35,7 +40,7 @@ constexpr int STAGE_DOUBLES = 2 * KT * LDS_T;           // A + B operand chunk
 constexpr int RBUF_DOUBLES = KT * LDS_T;                // one chunk of the post-multiplier
 constexpr int NRBUF = 4;                                // ring depth of the post-multiplier chunks
 constexpr int N_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (N_CONSUMER_WARPS + 1) * 32;
+constexpr int GEMM_THREADS = (N_CONSUMER_WARPS + 4) * 32;  // two consumer warpgroups + the producer's warpgroup
 static_assert(2 * NSTAGE + 2 * NRBUF <= 16, "barrier block holds 16 mbarriers");
 static_assert(NSTAGE * STAGE_DOUBLES == NB * LDS_T, "T tile must exactly reuse the stage ring");
 constexpr size_t GEMM_SMEM = (size_t)(NSTAGE * STAGE_DOUBLES + NRBUF * RBUF_DOUBLES) * sizeof(double) + 16 * sizeof(uint64_t);
@@ -346,7 +351,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
   const int nchunks = (tc.kb1 - tc.kb0) * (NB / KT) - ((tc.kb1 == g.J && tc.kb1 > tc.kb0) ? (NB / KT - last_kb_chunks) : 0);
   const int rows_valid = (tc.i == g.J - 1) ? nvl : NB;            // valid output rows of this tile
 
-  if (warp == N_CONSUMER_WARPS) {
+  if (warp >= N_CONSUMER_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // whole producer warpgroup; frees registers for the consumers
+    if (warp != N_CONSUMER_WARPS) return;
     // ===================== producer warp =====================
     int stage = 0; uint32_t phase = 0;
     int rissued = 0;
@@ -383,6 +390,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
     if (tc.post) for (; rissued < NB / KT; ++rissued) issue_r(rissued);
     return;
   }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // consumer warpgroups
   if (rows_valid == NB) consume_tile<false>(g, tc, stages, rbuf, full, empty, rfull, rempty, gp, nchunks, rows_valid);
   else consume_tile<true>(g, tc, stages, rbuf, full, empty, rfull, rempty, gp, nchunks, rows_valid);
 }
