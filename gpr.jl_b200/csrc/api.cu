@@ -55,15 +55,19 @@ static void free_batch(gprb_batch* b) {
   delete b;
 }
 
-// Enqueue one full evaluation of the GPs in list[off .. off+count) on `st`.
-static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, cudaStream_t st, bool prof) {
+// Enqueue one evaluation of the GPs in list[off .. off+count) on `st`: assembly, Cholesky and solve for all of them,
+// inverse + fused gradient for the first `ngrad` entries of the segment (the host orders value+gradient GPs first).
+static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, cudaStream_t st, bool prof) {
   if (count <= 0) return 0;
+  const bool with_grad = ngrad > 0;
   const int32_t* list = b->list + off;
   const int J = b->J;
   const int64_t ms = b->npad * b->npad, dstride = (int64_t)J * NB * NB;
   int rc;
   int64_t& launches = b->ctx->launches;
+  int gcount = count;  // GPs per tile-GEMM launch (count for the factorisation, ngrad for the inverse)
   auto gemm = [&](const GemmArgs& a, int ntiles) -> int {
+    const int count = gcount;
     if (!prof) return launch_tile_gemm(a, ntiles, count, st);
     while ((int)b->gemm_ev.size() < b->gemm_ev_used + 2) {
       cudaEvent_t e;
@@ -111,6 +115,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
   if (prof) cudaEventRecord(b->ev[1], st);
   const int nv = (int)((b->n + KT - 1) / KT * KT);
   GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, b->KinvD, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG, nv};
+  ga.fail = b->fail;
   DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
   for (int j = 0; j < J; ++j) {
     ga.step = j; ga.mode = GEMM_CHOL_DIAG;
@@ -132,6 +137,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
   if (prof) cudaEventRecord(b->ev[3], st);
   if (with_grad) {
     ga.Cin = nullptr;
+    gcount = ngrad;
     for (int i = 1; i < J; ++i) {
       ga.step = i; ga.mode = GEMM_TRTRI_ROW; ga.Cout = b->Lm;
       if ((rc = gemm(ga, i))) return rc;
@@ -143,51 +149,68 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, bool with_grad, c
     if (prof) cudaEventRecord(b->ev[4], st);
     GradArgs gr{b->Xtptr, b->theta, b->A, b->KinvD, b->alpha, b->grad_part, b->grad, b->fail, list, ms, dstride,
                 (int)b->n, (int)b->npad, b->d, J, b->kind};
-    if ((rc = launch_grad(gr, count, st))) return rc;
+    if ((rc = launch_grad(gr, ngrad, st))) return rc;
     launches += 2;
     if (prof) cudaEventRecord(b->ev[5], st);
   }
   return 0;
 }
 
-// Run the pipeline over the first `count` entries of b->list, split over the batch's streams so the serial
-// diagonal-block kernels of one group overlap the DMMA tiles of another.  Joins everything on stream[0].
-static int run_pipeline(gprb_batch* b, int count, bool with_grad) {
+// One stream group of an evaluation pass: list[off .. off+count), the first ngrad of them with gradient.
+struct Group { int off, count, ngrad; };
+
+// Order the active GPs of a pass into stream groups inside list_host: the value+gradient GPs and the value-only GPs
+// are each dealt evenly over the groups (equal work per stream), gradient GPs first inside every group.
+static std::vector<Group> build_groups(gprb_batch* b, const std::vector<int32_t>& grad_gps, const std::vector<int32_t>& val_gps) {
+  const int total = (int)(grad_gps.size() + val_gps.size());
+  const int S = (b->profiling || total < 8 || b->nstreams == 1) ? 1 : b->nstreams;
+  std::vector<Group> groups;
+  int off = 0;
+  for (int s = 0; s < S; ++s) {
+    const int g0 = (int)((int64_t)grad_gps.size() * s / S), g1 = (int)((int64_t)grad_gps.size() * (s + 1) / S);
+    const int v0 = (int)((int64_t)val_gps.size() * s / S), v1 = (int)((int64_t)val_gps.size() * (s + 1) / S);
+    Group g{off, (g1 - g0) + (v1 - v0), g1 - g0};
+    for (int k = g0; k < g1; ++k) b->list_host[off++] = grad_gps[k];
+    for (int k = v0; k < v1; ++k) b->list_host[off++] = val_gps[k];
+    if (g.count > 0) groups.push_back(g);
+  }
+  return groups;
+}
+
+// Run one pass: every group on its own stream so the serial diagonal-block kernels of one group overlap the DMMA
+// tiles of another.  Joins everything on stream[0].
+static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
   int rc;
-  if (b->profiling || count < 8 || b->nstreams == 1) {
-    if ((rc = enqueue_pipeline(b, 0, count, with_grad, b->stream[0], b->profiling))) return rc;
-    if (b->profiling) {
-      GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
-      float ms = 0.f;
-      const int last = with_grad ? 5 : 3;
-      for (int s = 0; s < 5; ++s) b->stage_ms[s] = 0.0;
-      for (int s = 0; s < last; ++s) {
-        GPRB_CUDA(cudaEventElapsedTime(&ms, b->ev[s], b->ev[s + 1]));
-        b->stage_ms[s] = ms;
-      }
-      GPRB_CUDA(cudaEventElapsedTime(&ms, b->ev[0], b->ev[last]));
-      b->stage_ms[5] = ms;
-      double gsum = 0.0;
-      for (int k = 0; k + 1 < b->gemm_ev_used; k += 2) {
-        GPRB_CUDA(cudaEventElapsedTime(&ms, b->gemm_ev[k], b->gemm_ev[k + 1]));
-        gsum += ms;
-      }
-      b->stage_ms[6] = gsum;
-      b->stage_ms[7] = b->gemm_ev_used / 2;
-      b->gemm_ms.clear();
-      for (int k = 0; k + 1 < b->gemm_ev_used; k += 2) {
-        GPRB_CUDA(cudaEventElapsedTime(&ms, b->gemm_ev[k], b->gemm_ev[k + 1]));
-        b->gemm_ms.push_back(ms);
-      }
+  if (groups.empty()) return 0;
+  if (b->profiling) {
+    const Group& g = groups[0];
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, b->stream[0], true))) return rc;
+    GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+    float ms = 0.f;
+    const int last = g.ngrad > 0 ? 5 : 3;
+    for (int s = 0; s < 5; ++s) b->stage_ms[s] = 0.0;
+    for (int s = 0; s < last; ++s) {
+      GPRB_CUDA(cudaEventElapsedTime(&ms, b->ev[s], b->ev[s + 1]));
+      b->stage_ms[s] = ms;
     }
+    GPRB_CUDA(cudaEventElapsedTime(&ms, b->ev[0], b->ev[last]));
+    b->stage_ms[5] = ms;
+    double gsum = 0.0;
+    b->gemm_ms.clear();
+    for (int k = 0; k + 1 < b->gemm_ev_used; k += 2) {
+      GPRB_CUDA(cudaEventElapsedTime(&ms, b->gemm_ev[k], b->gemm_ev[k + 1]));
+      gsum += ms;
+      b->gemm_ms.push_back(ms);
+    }
+    b->stage_ms[6] = gsum;
+    b->stage_ms[7] = b->gemm_ev_used / 2;
     return 0;
   }
-  const int S = b->nstreams;
   GPRB_CUDA(cudaEventRecord(b->join[0], b->stream[0]));
-  for (int s = 0; s < S; ++s) {
-    const int lo = (int)((int64_t)count * s / S), hi = (int)((int64_t)count * (s + 1) / S);
+  for (size_t s = 0; s < groups.size(); ++s) {
+    const Group& g = groups[s];
     if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(b->stream[s], b->join[0], 0));
-    if ((rc = enqueue_pipeline(b, lo, hi - lo, with_grad, b->stream[s], false))) return rc;
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, b->stream[s], false))) return rc;
     if (s > 0) {
       GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
       GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
@@ -196,47 +219,125 @@ static int run_pipeline(gprb_batch* b, int count, bool with_grad) {
   return 0;
 }
 
-static int upload_list(gprb_batch* b, int count) {
-  GPRB_CUDA(cudaMemcpyAsync(b->list, b->list_host, sizeof(int32_t) * count, cudaMemcpyHostToDevice, b->stream[0]));
+// ONE pipeline pass over the GPs with mode != 0 (theta already on the device).  retry[gp] != 0: the GP's previous
+// pass failed its factorisation - its cumulative jitter grows by 1e-6 tr(K)/n (make_posdef!) instead of being reset.
+// Afterwards: info[gp] final for the GPs that are done, pending[gp] = 1 for those that need another retry pass.
+static int eval_pass(gprb_batch* b, const uint8_t* mode, const uint8_t* retry, std::vector<int32_t>& info,
+                     std::vector<uint8_t>& pending) {
+  int rc;
+  const int B = b->B;
+  if ((int)b->tries.size() != B) b->tries.assign(B, 0);
+  pending.assign(B, 0);
+  std::vector<int32_t> grad_gps, val_gps;
+  int nfresh = 0, nretry = 0;
+  int32_t* aux = b->list_host + B;  // fresh GPs from the front, retried GPs from the back
+  for (int i = 0; i < B; ++i) {
+    if (!mode[i]) continue;
+    (mode[i] == 2 ? grad_gps : val_gps).push_back(i);
+    if (retry && retry[i]) aux[B - 1 - nretry++] = i;
+    else { aux[nfresh++] = i; b->tries[i] = 0; }
+  }
+  const int count = (int)(grad_gps.size() + val_gps.size());
+  if (count == 0) return 0;
+  const std::vector<Group> groups = build_groups(b, grad_gps, val_gps);
+  GPRB_CUDA(cudaMemcpyAsync(b->list, b->list_host, sizeof(int32_t) * 2 * B, cudaMemcpyHostToDevice, b->stream[0]));
+  if (nfresh) {
+    k_reset_jitter<<<(nfresh + 127) / 128, 128, 0, b->stream[0]>>>(b->jitter, b->list + B, nfresh);
+    GPRB_CUDA(cudaGetLastError());
+  }
+  if (nretry && (rc = launch_add_jitter(b->theta, b->jitter, b->list + 2 * B - nretry, b->d, nretry, b->stream[0]))) return rc;
+  if ((rc = run_pipeline(b, groups))) return rc;
+  GPRB_CUDA(cudaMemcpyAsync(b->fail_host, b->fail, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, b->stream[0]));
+  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+  if (getenv("GPRB200_LBFGS_TRACE")) {  // where do failed factorisations break down? (first bad pivot / n)
+    double sum = 0; int nf = 0;
+    for (int gp = 0; gp < B; ++gp)
+      if (mode[gp] && b->fail_host[gp] > 0) { sum += (double)b->fail_host[gp] / (double)b->n; ++nf; }
+    if (nf) fprintf(stderr, "  pass: %d of %d factorisations failed, mean failing pivot at %.2f n\n", nf, count, sum / nf);
+  }
+  for (int pass = 0; pass < 2; ++pass)
+    for (int gp : (pass == 0 ? grad_gps : val_gps)) {
+      const int f = b->fail_host[gp];
+      if (f == 0) info[gp] = b->tries[gp];
+      else if (f < 0) info[gp] = -2;
+      else if (b->tries[gp] >= MAX_JITTER) info[gp] = -1;
+      else { b->tries[gp]++; pending[gp] = 1; b->state_ok[gp] = 0; b->inv_ok[gp] = 0; b->v_ok[gp] = 0; continue; }
+      b->state_ok[gp] = info[gp] >= 0;
+      b->inv_ok[gp] = pass == 0 && info[gp] >= 0;
+      b->v_ok[gp] = b->inv_ok[gp];
+    }
   return 0;
 }
 
-// Shared tail of gprb_eval / gprb_eval_device: pipeline + make_posdef! retry loop.  list_host[0..count) holds the
-// active GPs.  On return info_host (pinned fail_host reused) holds per-GP info for ALL B (inactive untouched = 0).
-static int evaluate_active(gprb_batch* b, int count, bool with_grad, std::vector<int32_t>& info) {
-  int rc;
+// Evaluation with the make_posdef! retry loop inside (gprb_eval / gprb_eval_mixed / gprb_eval_device): passes are
+// repeated for the GPs that still need a jitter until none is pending.
+static int evaluate_modes(gprb_batch* b, const uint8_t* mode, std::vector<int32_t>& info) {
   info.assign(b->B, 0);
-  if (count == 0) return 0;
-  if ((rc = upload_list(b, count))) return rc;
-  k_reset_jitter<<<(count + 127) / 128, 128, 0, b->stream[0]>>>(b->jitter, b->list, count);
-  GPRB_CUDA(cudaGetLastError());
-  if ((rc = run_pipeline(b, count, with_grad))) return rc;
-  std::vector<int32_t> tries(b->B, 0);
-  for (int attempt = 0;; ++attempt) {
-    GPRB_CUDA(cudaMemcpyAsync(b->fail_host, b->fail, sizeof(int32_t) * b->B, cudaMemcpyDeviceToHost, b->stream[0]));
-    GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
-    // list_host still holds the GPs evaluated in the last pass (first `count` entries)
-    int nretry = 0;
-    std::vector<int32_t> again;
-    for (int k = 0; k < count; ++k) {
-      const int gp = b->list_host[k];
-      const int f = b->fail_host[gp];
-      if (f == 0) info[gp] = tries[gp];
-      else if (f < 0) info[gp] = -2;
-      else if (tries[gp] >= MAX_JITTER) info[gp] = -1;
-      else { tries[gp]++; again.push_back(gp); ++nretry; continue; }
-      b->state_ok[gp] = info[gp] >= 0;
-      b->inv_ok[gp] = with_grad && info[gp] >= 0;
-      b->v_ok[gp] = b->inv_ok[gp];
+  std::vector<uint8_t> cur(mode, mode + b->B), retry(b->B, 0), pending;
+  for (;;) {
+    int rc = eval_pass(b, cur.data(), retry.data(), info, pending);
+    if (rc) return rc;
+    bool any = false;
+    for (int i = 0; i < b->B; ++i) {
+      cur[i] = pending[i] ? cur[i] : 0;
+      retry[i] = pending[i];
+      any = any || pending[i];
     }
-    if (nretry == 0) break;
-    for (int k = 0; k < nretry; ++k) b->list_host[k] = again[k];
-    count = nretry;
-    if ((rc = upload_list(b, count))) return rc;
-    if ((rc = launch_add_jitter(b->theta, b->jitter, b->list, b->d, count, b->stream[0]))) return rc;
-    if ((rc = run_pipeline(b, count, with_grad))) return rc;
+    if (!any) return 0;
+  }
+}
+
+// theta rows of the listed GPs -> device (pinned staging, one strided copy per contiguous run of GP indices)
+static int upload_theta_rows(gprb_batch* b, const double* theta, const std::vector<int32_t>& act) {
+  const int P = b->P, count = (int)act.size();
+  double* st = b->stage_host;
+  for (int k = 0; k < count; ++k) memcpy(st + (size_t)k * P, theta + (size_t)act[k] * P, sizeof(double) * P);
+  for (int k = 0; k < count;) {
+    int k2 = k + 1;
+    while (k2 < count && act[k2] == act[k2 - 1] + 1) ++k2;
+    GPRB_CUDA(cudaMemcpyAsync(b->theta + (size_t)act[k] * P, st + (size_t)k * P, sizeof(double) * P * (k2 - k),
+                              cudaMemcpyHostToDevice, b->stream[0]));
+    k = k2;
   }
   return 0;
+}
+
+// mll (+ grad rows of the mode-2 GPs) of the finished GPs -> host arrays
+static int download_results(gprb_batch* b, const uint8_t* mode, const std::vector<int32_t>& info, const uint8_t* skip,
+                            double* mll, double* grad, int32_t* info_out) {
+  const int B = b->B, P = b->P;
+  bool any_grad = false;
+  for (int i = 0; i < B; ++i) any_grad = any_grad || (mode[i] == 2 && !(skip && skip[i]));
+  double* res = b->stage_host;  // [B] mll then [B*P] grad
+  GPRB_CUDA(cudaMemcpyAsync(res, b->mll, sizeof(double) * B, cudaMemcpyDeviceToHost, b->stream[0]));
+  if (any_grad) GPRB_CUDA(cudaMemcpyAsync(res + B, b->grad, sizeof(double) * B * P, cudaMemcpyDeviceToHost, b->stream[0]));
+  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
+  const double ninf = -std::numeric_limits<double>::infinity(), qnan = std::numeric_limits<double>::quiet_NaN();
+  for (int gp = 0; gp < B; ++gp) {
+    if (!mode[gp] || (skip && skip[gp])) continue;
+    info_out[gp] = info[gp];
+    const bool ok = info[gp] >= 0;
+    mll[gp] = ok ? res[gp] : ninf;
+    if (mode[gp] == 2)
+      for (int p = 0; p < P; ++p) grad[(size_t)gp * P + p] = ok ? res[B + (size_t)gp * P + p] : qnan;
+  }
+  return 0;
+}
+
+int eval_pass_host(gprb_batch* b, const double* theta, const uint8_t* mode, const uint8_t* retry, double* mll, double* grad,
+                   int32_t* info_out, uint8_t* pending_out) {
+  GPRB_REQUIRE(b && theta && mode && mll && grad && info_out && pending_out, "eval_pass_host: NULL argument");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  std::vector<int32_t> fresh;
+  for (int i = 0; i < b->B; ++i)
+    if (mode[i] && !(retry && retry[i])) fresh.push_back(i);
+  int rc = upload_theta_rows(b, theta, fresh);
+  if (rc) return rc;
+  std::vector<int32_t> info(b->B, 0);
+  std::vector<uint8_t> pending;
+  if ((rc = eval_pass(b, mode, retry, info, pending))) return rc;
+  memcpy(pending_out, pending.data(), b->B);
+  return download_results(b, mode, info, pending_out, mll, grad, info_out);
 }
 
 }  // namespace gprb
@@ -409,11 +510,11 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
         (rc = dev_alloc(&b->alpha, (size_t)B * b->npad)) || (rc = dev_alloc(&b->zbuf, (size_t)B * b->npad)) ||
         (rc = dev_alloc(&b->jitter, B)) || (rc = dev_alloc(&b->logdet_part, (size_t)B * b->J)) ||
         (rc = dev_alloc(&b->fail, B)) || (rc = dev_alloc(&b->mll, B)) || (rc = dev_alloc(&b->grad, (size_t)B * b->P)) ||
-        (rc = dev_alloc(&b->grad_part, (size_t)B * ntiles * GRAD_PARTS_PER_TILE * b->P)) || (rc = dev_alloc(&b->list, B)))
+        (rc = dev_alloc(&b->grad_part, (size_t)B * ntiles * GRAD_PARTS_PER_TILE * b->P)) || (rc = dev_alloc(&b->list, 2 * (size_t)B)))
       break;
     b->stage_doubles = (int64_t)B * (b->P + 2);
     cudaError_t e;
-    if ((e = cudaMallocHost((void**)&b->list_host, sizeof(int32_t) * B)) != cudaSuccess ||
+    if ((e = cudaMallocHost((void**)&b->list_host, sizeof(int32_t) * 2 * B)) != cudaSuccess ||
         (e = cudaMallocHost((void**)&b->fail_host, sizeof(int32_t) * B)) != cudaSuccess ||
         (e = cudaMallocHost((void**)&b->stage_host, sizeof(double) * b->stage_doubles)) != cudaSuccess) {
       rc = cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
@@ -479,40 +580,29 @@ int gprb_last_stage_ms(gprb_batch* b, double out[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------
+int gprb_eval_mixed(gprb_batch* b, const double* theta, const uint8_t* mode, double* mll, double* grad, int32_t* info) {
+  GPRB_REQUIRE(b && theta && mode && mll && info, "gprb_eval_mixed: NULL argument");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  bool any_grad = false;
+  std::vector<int32_t> act;
+  for (int i = 0; i < b->B; ++i) {
+    GPRB_REQUIRE(mode[i] <= 2, "gprb_eval_mixed: mode must be 0 (skip), 1 (value) or 2 (value+gradient)");
+    if (mode[i]) act.push_back(i);
+    any_grad = any_grad || mode[i] == 2;
+  }
+  GPRB_REQUIRE(!any_grad || grad, "gprb_eval_mixed: a GP asks for its gradient but grad is NULL");
+  int rc = upload_theta_rows(b, theta, act);
+  if (rc) return rc;
+  std::vector<int32_t> inf;
+  if ((rc = evaluate_modes(b, mode, inf))) return rc;
+  return download_results(b, mode, inf, nullptr, mll, grad, info);
+}
+
 int gprb_eval(gprb_batch* b, const double* theta, const uint8_t* active, double* mll, double* grad, int32_t* info) {
   GPRB_REQUIRE(b && theta && mll && info, "gprb_eval: NULL argument");
-  GPRB_CUDA(cudaSetDevice(b->ctx->device));
-  const int B = b->B, P = b->P;
-  int count = 0;
-  for (int i = 0; i < B; ++i)
-    if (!active || active[i]) b->list_host[count++] = i;
-  // stage theta of the active GPs (pinned) and scatter with one strided copy per contiguous run
-  double* st = b->stage_host;
-  for (int k = 0; k < count; ++k) memcpy(st + (size_t)k * P, theta + (size_t)b->list_host[k] * P, sizeof(double) * P);
-  for (int k = 0; k < count;) {
-    int k2 = k + 1;
-    while (k2 < count && b->list_host[k2] == b->list_host[k2 - 1] + 1) ++k2;
-    GPRB_CUDA(cudaMemcpyAsync(b->theta + (size_t)b->list_host[k] * P, st + (size_t)k * P, sizeof(double) * P * (k2 - k),
-                              cudaMemcpyHostToDevice, b->stream[0]));
-    k = k2;
-  }
-  std::vector<int32_t> inf;
-  std::vector<int32_t> act(b->list_host, b->list_host + count);
-  int rc = evaluate_active(b, count, grad != nullptr, inf);
-  if (rc) return rc;
-  double* res = b->stage_host;  // [B] mll then [B*P] grad
-  GPRB_CUDA(cudaMemcpyAsync(res, b->mll, sizeof(double) * B, cudaMemcpyDeviceToHost, b->stream[0]));
-  if (grad) GPRB_CUDA(cudaMemcpyAsync(res + B, b->grad, sizeof(double) * B * P, cudaMemcpyDeviceToHost, b->stream[0]));
-  GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
-  const double ninf = -std::numeric_limits<double>::infinity(), qnan = std::numeric_limits<double>::quiet_NaN();
-  for (int gp : act) {
-    info[gp] = inf[gp];
-    const bool ok = inf[gp] >= 0;
-    mll[gp] = ok ? res[gp] : ninf;
-    if (grad)
-      for (int p = 0; p < P; ++p) grad[(size_t)gp * P + p] = ok ? res[B + (size_t)gp * P + p] : qnan;
-  }
-  return GPRB_OK;
+  std::vector<uint8_t> mode(b->B);
+  for (int i = 0; i < b->B; ++i) mode[i] = (!active || active[i]) ? (grad ? 2 : 1) : 0;
+  return gprb_eval_mixed(b, theta, mode.data(), mll, grad, info);
 }
 
 int gprb_eval_device(gprb_batch* b, const double* theta_dev, double* mll_dev, double* grad_dev, int32_t* info_dev,
@@ -525,9 +615,9 @@ int gprb_eval_device(gprb_batch* b, const double* theta_dev, double* mll_dev, do
   GPRB_CUDA(cudaEventRecord(b->join[0], user));
   GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[0], 0));
   GPRB_CUDA(cudaMemcpyAsync(b->theta, theta_dev, sizeof(double) * B * P, cudaMemcpyDeviceToDevice, b->stream[0]));
-  for (int i = 0; i < B; ++i) b->list_host[i] = i;
+  std::vector<uint8_t> mode(B, grad_dev ? 2 : 1);
   std::vector<int32_t> inf;
-  int rc = evaluate_active(b, B, grad_dev != nullptr, inf);
+  int rc = evaluate_modes(b, mode.data(), inf);
   if (rc) return rc;
   GPRB_CUDA(cudaMemcpyAsync(mll_dev, b->mll, sizeof(double) * B, cudaMemcpyDeviceToDevice, b->stream[0]));
   if (grad_dev) GPRB_CUDA(cudaMemcpyAsync(grad_dev, b->grad, sizeof(double) * B * P, cudaMemcpyDeviceToDevice, b->stream[0]));

@@ -35,6 +35,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     }                                    \
   } while (0)
 
+// One evaluation pass for the batched optimiser (api.cu): like gprb_eval_mixed, but the make_posdef! retries are NOT
+// looped inside - a GP whose factorisation failed comes back with pending[gp] = 1 and is re-submitted (retry[gp] = 1,
+// same theta, one more jitter) together with the next round's evaluations of the other GPs.
+int eval_pass_host(gprb_batch* b, const double* theta, const uint8_t* mode, const uint8_t* retry, double* mll, double* grad,
+                   int32_t* info, uint8_t* pending);
+
 }  // namespace gprb
 
 struct gprb_ctx {
@@ -85,8 +91,9 @@ struct gprb_batch {
   double* mll = nullptr;          // [B]
   double* grad = nullptr;         // [B][P]
   double* grad_part = nullptr;    // [B][ntiles][P+1] per-tile partial sums (deterministic 2-pass reduction)
-  int32_t* list = nullptr;        // [B] compact list of GP indices a launch works on
-  int32_t* list_host = nullptr;   // pinned
+  int32_t* list = nullptr;        // [2B] compact lists of GP indices: [0,B) the stream groups of a pass, [B,2B) the fresh / retried GPs
+  int32_t* list_host = nullptr;   // pinned, same layout
+  std::vector<int32_t> tries;     // per GP: make_posdef! jitter additions of the evaluation in progress
   int32_t* fail_host = nullptr;   // pinned
   double* stage_host = nullptr;   // pinned staging for theta / results
   int64_t stage_doubles = 0;

@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(w + MAX_D);
   double* red = Ki;                                   // [(d + 2)][NT] <= 2 * CW * NB doubles for d <= 62
   const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  if (g.fail[gp] != 0) return;  // failed factorisation: k_grad_reduce reports NaN, nothing to sum
   const int tile = blockIdx.x / NQ, cq = blockIdx.x - tile * NQ;
   int ti, tj;
   lower_tile(tile, ti, tj);

@@ -23,6 +23,7 @@ struct GemmArgs {
   double* Tm = nullptr;
   int64_t t_stride = 0;
   int ldt = 0;
+  const int32_t* fail = nullptr;     // [B] per-GP failure flag: tiles of a GP whose factorisation already broke down exit at once
   unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)
 };
 

@@ -5,9 +5,12 @@
 //     (examples/maximal_coordinates/CPnoise.jl:41 and every other experiment file)
 // i.e. Optim 1.4.1 LBFGS(m=10, InitialStatic(alpha=1), scaleinvH0=true) + LineSearches 7.1.1 BackTracking
 // (same state machine as oracle/lbfgs_oracle.py), but for B GPs at once:
-// every round issues ONE value-only batch (all GPs currently inside a line search) and ONE value+gradient
-// batch (all GPs that just accepted a step), each through gprb_eval with a per-GP active mask.
+// every round issues ONE mixed pass through gprb_eval_mixed - a value-only evaluation for each GP inside a line
+// search and a value+gradient evaluation for each GP that accepted a step in the previous round.  Per GP the
+// sequence of evaluations is exactly the scalar algorithm's; only the batching across GPs differs.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -19,8 +22,11 @@
 
 namespace gprb {
 
-// objective(theta[B*P], active[B], f[B], g[B*P] or nullptr) -> rc ; f = -mll (+Inf on failure), g = -dmll
-using Objective = std::function<int(const double*, const uint8_t*, double*, double*)>;
+// objective(theta[B*P], mode[B] (0 skip / 1 value / 2 value+gradient), retry[B], f[B], g[B*P], pending[B]) -> rc ;
+// f = -mll (+Inf on failure), g = -dmll for the mode-2 GPs.  pending[b] = 1: the evaluation of GP b is not finished
+// (its factorisation needs another make_posdef! jitter) - the caller re-submits it with retry[b] = 1 and the same
+// theta in its next pass, next to the other GPs' new evaluations, instead of stalling the whole batch on it.
+using Objective = std::function<int(const double*, const uint8_t*, const uint8_t*, double*, double*, uint8_t*)>;
 
 struct GpState {
   std::vector<double> x, g, g_prev, s, dx, x_trial;
@@ -79,9 +85,21 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<GpState> S(B);
   std::vector<double> theta((size_t)B * P), f(B), g((size_t)B * P);
-  std::vector<uint8_t> act(B, 1);
+  std::vector<uint8_t> act(B, 2);
   memcpy(theta.data(), theta_inout, sizeof(double) * B * P);
-  int rc = obj(theta.data(), act.data(), f.data(), g.data());
+  std::vector<uint8_t> retry(B, 0), pending(B, 0);
+  // evaluate `act` for everyone, looping until no GP has a retry pending (initial and final evaluations)
+  auto eval_all = [&]() -> int {
+    std::vector<uint8_t> cur(act), rt(B, 0), pd(B, 0);
+    for (;;) {
+      int r = obj(theta.data(), cur.data(), rt.data(), f.data(), g.data(), pd.data());
+      if (r) return r;
+      bool any = false;
+      for (int b = 0; b < B; ++b) { cur[b] = pd[b] ? cur[b] : 0; rt[b] = pd[b]; any = any || pd[b]; }
+      if (!any) return 0;
+    }
+  };
+  int rc = eval_all();
   if (rc) return rc;
   for (int b = 0; b < B; ++b) {
     GpState& st = S[b];
@@ -103,7 +121,7 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
   };
   bool timed_out = false;
   for (;;) {
-    // ---- 1. search directions for GPs starting an iteration (update_state! up to the line search)
+    // ---- 1. search directions for GPs starting an iteration (update_state! up to the line search): host only
     for (int b = 0; b < B; ++b) {
       GpState& st = S[b];
       if (st.phase != GpState::NEED_DIR) continue;
@@ -123,17 +141,35 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
       set_trial(st, st.a2);
       st.phase = GpState::IN_LS;
     }
-    // ---- 2. one value-only batch for everything inside a line search
-    int nls = 0;
+    // ---- 2. ONE mixed pass: value-only at the trial point of every GP inside a line search, value+gradient at the
+    //         accepted point of every GP that left its line search in the previous round (update_g!)
+    int nact = 0;
     for (int b = 0; b < B; ++b) {
-      act[b] = S[b].phase == GpState::IN_LS;
-      if (act[b]) { memcpy(&theta[(size_t)b * P], S[b].x_trial.data(), sizeof(double) * P); ++nls; }
+      GpState& st = S[b];
+      act[b] = st.phase == GpState::IN_LS ? 1 : st.phase == GpState::NEED_GRAD ? 2 : 0;
+      if (act[b] == 1) memcpy(&theta[(size_t)b * P], st.x_trial.data(), sizeof(double) * P);
+      else if (act[b] == 2)
+        for (int p = 0; p < P; ++p) theta[(size_t)b * P + p] = st.x[p] + st.dx[p];
+      nact += act[b] != 0;
     }
-    if (nls) {
-      if ((rc = obj(theta.data(), act.data(), f.data(), nullptr))) return rc;
-      for (int b = 0; b < B; ++b) {
-        if (!act[b]) continue;
-        GpState& st = S[b];
+    if (nact == 0) break;
+    const auto tr0 = std::chrono::steady_clock::now();
+    if ((rc = obj(theta.data(), act.data(), retry.data(), f.data(), g.data(), pending.data()))) return rc;
+    for (int b = 0; b < B; ++b) {  // unfinished evaluations ride along with the next round
+      retry[b] = pending[b];
+      if (pending[b]) act[b] = 0;
+    }
+    if (getenv("GPRB200_LBFGS_TRACE")) {  // per-round trace: GPs in the value-only / value+gradient sets and the round time
+      int nv = 0, ng = 0, np = 0;
+      for (int b = 0; b < B; ++b) { nv += act[b] == 1; ng += act[b] == 2; np += pending[b]; }
+      fprintf(stderr, "lbfgs round: value %d grad %d retry-pending %d  %.2f ms\n", nv, ng, np,
+              1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count());
+    }
+    if (o.time_limit > 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > o.time_limit)
+      timed_out = true;
+    for (int b = 0; b < B; ++b) {
+      GpState& st = S[b];
+      if (act[b] == 1) {
         st.f_calls++;
         st.phi1 = f[b];
         // BackTracking: "halve until finite" pre-loop
@@ -162,28 +198,11 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
           set_trial(st, st.a2);
           continue;
         }
-        // accepted
+        // accepted: the gradient at the new point is requested in the next round
         for (int p = 0; p < P; ++p) st.dx[p] = st.a2 * st.s[p];
         st.f_prev = st.fx;
         st.phase = GpState::NEED_GRAD;
-      }
-    }
-    // ---- 3. one value+gradient batch at the accepted points (update_g!: value_gradient! at the new x)
-    int ng = 0;
-    for (int b = 0; b < B; ++b) {
-      act[b] = S[b].phase == GpState::NEED_GRAD;
-      if (act[b]) {
-        for (int p = 0; p < P; ++p) theta[(size_t)b * P + p] = S[b].x[p] + S[b].dx[p];
-        ++ng;
-      }
-    }
-    if (ng) {
-      if ((rc = obj(theta.data(), act.data(), f.data(), g.data()))) return rc;
-      const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      if (o.time_limit > 0 && elapsed > o.time_limit) timed_out = true;
-      for (int b = 0; b < B; ++b) {
-        if (!act[b]) continue;
-        GpState& st = S[b];
+      } else if (act[b] == 2) {
         st.fg_calls++;
         double dxmax = 0.0;
         for (int p = 0; p < P; ++p) {
@@ -212,23 +231,11 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
         st.phase = GpState::NEED_DIR;
         if (st.iteration >= o.iterations) st.phase = GpState::DONE;
         if (o.max_evals > 0 && st.f_calls + st.fg_calls >= o.max_evals) st.phase = GpState::DONE;
-        if (timed_out) st.phase = GpState::DONE;
       }
     }
-    if (timed_out)
-      for (int b = 0; b < B; ++b)
-        if (S[b].phase == GpState::NEED_DIR) S[b].phase = GpState::DONE;
-    bool any = false;
-    for (int b = 0; b < B; ++b) any = any || (S[b].phase != GpState::DONE);
-    if (!any) break;
-    if (!nls && !ng) break;  // defensive: no progress possible
-    if (o.time_limit > 0 && !timed_out) {
-      const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      if (elapsed > o.time_limit) {
-        timed_out = true;  // GPs still inside a line search keep their last accepted x
-        for (int b = 0; b < B; ++b) S[b].phase = GpState::DONE;
-        break;
-      }
+    if (timed_out) {  // Optim checks the time limit once per iteration: GPs keep their last accepted x
+      for (int b = 0; b < B; ++b) S[b].phase = GpState::DONE;
+      break;
     }
   }
   // ---- write the minimiser back and leave the device state evaluated there (optimize! -> update_target!)
@@ -236,7 +243,7 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
     memcpy(&theta[(size_t)b * P], S[b].x.data(), sizeof(double) * P);
     act[b] = 1;
   }
-  if ((rc = obj(theta.data(), act.data(), f.data(), nullptr))) return rc;
+  if ((rc = eval_all())) return rc;
   memcpy(theta_inout, theta.data(), sizeof(double) * B * P);
   for (int b = 0; b < B; ++b) {
     gprb_opt_result& r = results[b];
@@ -272,14 +279,14 @@ int gprb_optimize(gprb_batch* b, double* theta_inout, const gprb_lbfgs_opts* opt
   std::vector<double> mll(B), grad((size_t)B * P);
   std::vector<int32_t> info(B, 0), last_info(B, 0);
   // get_optim_target: objective = -mll, gradient = -dmll, +Inf when the evaluation fails (info < 0)
-  Objective obj = [&](const double* theta, const uint8_t* active, double* f, double* g) -> int {
-    int rc = gprb_eval(b, theta, active, mll.data(), g ? grad.data() : nullptr, info.data());
+  Objective obj = [&](const double* theta, const uint8_t* mode, const uint8_t* retry, double* f, double* g, uint8_t* pending) -> int {
+    int rc = eval_pass_host(b, theta, mode, retry, mll.data(), grad.data(), info.data(), pending);
     if (rc) return rc;
     for (int i = 0; i < B; ++i) {
-      if (active && !active[i]) continue;
+      if (!mode[i] || pending[i]) continue;
       last_info[i] = info[i];
       f[i] = info[i] < 0 ? INFINITY : -mll[i];
-      if (g)
+      if (mode[i] == 2)
         for (int p = 0; p < P; ++p) g[(size_t)i * P + p] = info[i] < 0 ? NAN : -grad[(size_t)i * P + p];
     }
     return 0;
@@ -298,9 +305,11 @@ int gprb_lbfgs_selftest(int32_t B, int32_t P, double* theta_inout, const gprb_lb
   GPRB_REQUIRE(theta_inout && results && B > 0 && P > 1, "gprb_lbfgs_selftest: bad argument");
   gprb_lbfgs_opts o;
   if (opts) o = *opts; else gprb_lbfgs_default_opts(&o);
-  Objective obj = [&](const double* theta, const uint8_t* active, double* f, double* g) -> int {
+  Objective obj = [&](const double* theta, const uint8_t* mode, const uint8_t*, double* f, double* gout, uint8_t* pending) -> int {
     for (int b = 0; b < B; ++b) {
-      if (active && !active[b]) continue;
+      pending[b] = 0;
+      if (!mode[b]) continue;
+      double* g = mode[b] == 2 ? gout : nullptr;
       const double* x = theta + (size_t)b * P;
       bool inside = true;
       for (int p = 0; p < P; ++p) inside = inside && fabs(x[p]) <= bound;

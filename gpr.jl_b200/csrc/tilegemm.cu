@@ -331,6 +331,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
   GPRB_TL(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  // A GP whose factorisation already hit a non-positive pivot (make_posdef! will retry it with more jitter) skips the
+  // rest of the failed attempt, like dpotrf stopping at the failing column.  The load overlaps the setup below.
+  const int failed = g.fail ? g.fail[gp] : 0;
   const TileCoord tc = tile_coord(g.mode, g.step, g.J, blockIdx.x);
   const int64_t npad = g.npad;
   const double* Lm = g.Lm + (int64_t)gp * g.mat_stride;
@@ -342,6 +345,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
     for (int s = 0; s < NRBUF; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], N_CONSUMER_WARPS); }
     mbar_fence_init();
   }
+  if (failed != 0) return;  // uniform over the CTA
   __syncthreads();
 
   // Padding skip: rows/cols >= nv (n rounded up to the 16-wide chunk) are never computed and never read.

@@ -365,6 +365,22 @@ class GPBatch:
                 gp.dmll = g[b].copy() if grad else None
         return mll, g, info
 
+    def eval_mixed(self, theta, mode):
+        """gprb_eval_mixed: mode[b] = 0 skip / 1 value only / 2 value + gradient, one pipeline pass for all of them.
+        -> (mll (B,), grad (B,P) with NaN rows where no gradient was asked, info (B,))."""
+        theta = as_f64(theta).reshape(self.B, self.P)
+        mode = np.ascontiguousarray(mode, dtype=np.uint8)
+        mll = np.full(self.B, np.nan)
+        g = np.full((self.B, self.P), np.nan)
+        info = np.zeros(self.B, dtype=np.int32)
+        self.lib.check(self.lib.dll.gprb_eval_mixed(self.handle, _d(theta), mode.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                    _d(mll), _d(g), info.ctypes.data_as(C.POINTER(C.c_int32))))
+        for b, gp in enumerate(self.gps):
+            if mode[b]:
+                gp.mll, gp.info = float(mll[b]), int(info[b])
+                gp.dmll = g[b].copy() if mode[b] == 2 else None
+        return mll, g, info
+
     def eval_device(self, theta_ptr, mll_ptr, grad_ptr=None, info_ptr=None, stream=0):
         """gprb_eval_device: theta (B,P) / mll (B,) / grad (B,P) / info (B,) are raw device pointers (ints, e.g.
         ``torch.Tensor.data_ptr()``); no payload crosses PCIe.  Ordered after ``stream`` (a cudaStream_t handle)."""

@@ -13,7 +13,7 @@ EXPORTS = [
     "gprb_version", "gprb_last_error", "gprb_init", "gprb_destroy", "gprb_device_info",
     "gprb_dataset_create", "gprb_dataset_update", "gprb_datasets_update", "gprb_dataset_destroy",
     "gprb_batch_create", "gprb_batch_set_targets", "gprb_batch_destroy",
-    "gprb_eval", "gprb_eval_device", "gprb_lbfgs_default_opts", "gprb_optimize", "gprb_lbfgs_selftest", "gprb_predict",
+    "gprb_eval", "gprb_eval_mixed", "gprb_eval_device", "gprb_lbfgs_default_opts", "gprb_optimize", "gprb_lbfgs_selftest", "gprb_predict",
     "gprb_get_K", "gprb_get_chol", "gprb_get_alpha", "gprb_get_Kinv",
     "gprb_set_profiling", "gprb_last_stage_ms", "gprb_last_gemm_launch_ms", "gprb_launch_count",
 ]
@@ -72,6 +72,7 @@ class Library:
         L.gprb_batch_set_targets.argtypes = [_vp, _dp]
         L.gprb_batch_destroy.argtypes = [_vp]
         L.gprb_eval.argtypes = [_vp, _dp, C.POINTER(C.c_uint8), _dp, _dp, C.POINTER(C.c_int32)]
+        L.gprb_eval_mixed.argtypes = [_vp, _dp, C.POINTER(C.c_uint8), _dp, _dp, C.POINTER(C.c_int32)]
         L.gprb_eval_device.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
         L.gprb_lbfgs_default_opts.argtypes = [C.POINTER(LbfgsOpts)]
         L.gprb_lbfgs_default_opts.restype = None

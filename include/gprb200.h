@@ -88,6 +88,12 @@ int gprb_batch_destroy(gprb_batch* batch);
  * After return, the factor, alpha and theta of every evaluated GP stay resident for gprb_predict. */
 int gprb_eval(gprb_batch* batch, const double* theta, const uint8_t* active, double* mll, double* grad, int32_t* info);
 
+/* Mixed pass: mode[b] = 0 skip, 1 value only, 2 value + gradient.  One pipeline pass evaluates the value-only and the
+ * value+gradient GPs together (factorisation for all, inverse + gradient for the mode-2 subset); this is what the
+ * batched optimiser issues once per round (line-search trials of some GPs next to the gradient evaluations of the
+ * GPs that just accepted a step).  grad may be NULL when no GP asks for mode 2; grad rows of other GPs are untouched. */
+int gprb_eval_mixed(gprb_batch* batch, const double* theta, const uint8_t* mode, double* mll, double* grad, int32_t* info);
+
 /* Same evaluation for ALL GPs with theta / outputs already in device memory: no payload crosses PCIe (only the
  * 4-byte per-GP status the make_posdef! retry loop needs).  Ordered after prior work on `stream` (a cudaStream_t);
  * complete on return.  grad_dev / info_dev may be NULL. */

@@ -284,6 +284,29 @@ def test_active_mask(gprb):
             assert rel(batch.alpha(b), oracle_all([tr], [thetas])[b]["state"]["alpha"]) <= 1e-8  # state kept
 
 
+def test_mixed_value_and_gradient_pass(gprb):
+    """gprb_eval_mixed (what the optimiser issues every round): value-only, value+gradient and skipped GPs in one pass."""
+    from gpr_jl_b200 import data
+    trials = data.make_config("CP", trials=3, n=150)
+    thetas = [np.tile(data.theta0("CP", tr["X"]), (4, 1)) + 0.1 * np.random.default_rng(t).standard_normal((4, 28))
+              for t, tr in enumerate(trials)]
+    batch = build_batch(gprb, trials, thetas)
+    mode = np.array([2, 1, 0, 2, 1, 1, 2, 0, 2, 2, 1, 0], dtype=np.uint8)
+    mll, grad, info = batch.eval_mixed(np.concatenate(thetas), mode)
+    for b, r in enumerate(oracle_all(trials, thetas)):
+        if mode[b] == 0:
+            assert np.isnan(mll[b]) and np.all(np.isnan(grad[b]))
+            continue
+        assert info[b] == 0 and abs(mll[b] - r["mll"]) <= 1e-8 * abs(r["mll"])
+        if mode[b] == 2:
+            assert rel(grad[b], r["grad"]) <= 1e-8
+            assert rel(batch.Kinv(b), r["state"]["Kinv"]) <= 1e-8
+        else:
+            assert np.all(np.isnan(grad[b]))
+            with pytest.raises(gprb.GprbError):
+                batch.Kinv(b)  # value-only state holds no inverse
+
+
 def test_multi_trial_batch_shares_datasets(gprb):
     from gpr_jl_b200 import data
     trials = data.make_config("CP", trials=3, n=200)
