@@ -57,7 +57,7 @@ static void free_batch(gprb_batch* b) {
 
 // Enqueue one evaluation of the GPs in list[off .. off+count) on `st`: assembly, Cholesky and solve for all of them,
 // inverse + fused gradient for the first `ngrad` entries of the segment (the host orders value+gradient GPs first).
-static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, cudaStream_t st, bool prof) {
+static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool right_looking, cudaStream_t st, bool prof) {
   if (count <= 0) return 0;
   const bool with_grad = ngrad > 0;
   const int32_t* list = b->list + off;
@@ -109,7 +109,10 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, cudaSt
 #endif
   };
   if (prof) { b->gemm_ev_used = 0; cudaEventRecord(b->ev[0], st); }
-  AssembleArgs aa{b->Xtptr, b->theta, b->jitter, b->A, b->fail, list, ms, (int)b->n, (int)b->npad, b->d, J, b->kind};
+  // Small passes are latency bound (one dependent chain of 3 J launches): they use the right-looking factorisation,
+  // whose launches are short and wide, instead of the left-looking one, whose k-loops grow with the column index.
+  AssembleArgs aa{b->Xtptr, b->theta, b->jitter, b->A, nullptr, b->fail, list, ms, (int)b->n, (int)b->npad, b->d, J, b->kind};
+  if (right_looking) aa.A2 = b->Lm;
   if ((rc = launch_assemble(aa, count, st))) return rc;
   ++launches;
   if (prof) cudaEventRecord(b->ev[1], st);
@@ -117,16 +120,26 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, cudaSt
   GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, b->KinvD, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG, nv};
   ga.fail = b->fail;
   DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
+  if (right_looking) ga.Cin = b->Lm;  // S lives (and is updated in place) in the lower tiles of Lm
   for (int j = 0; j < J; ++j) {
-    ga.step = j; ga.mode = GEMM_CHOL_DIAG;
-    if ((rc = gemm(ga, 1))) return rc;
+    ga.step = j;
+    if (!right_looking) {
+      ga.mode = GEMM_CHOL_DIAG;
+      if ((rc = gemm(ga, 1))) return rc;
+      ++launches;
+    }
     da.step = j;
     if ((rc = launch_diag_factor(da, count, st))) return rc;
-    launches += 2;
+    ++launches;
     if (j + 1 < J) {
-      ga.mode = GEMM_CHOL_COL;
+      ga.mode = right_looking ? GEMM_CHOL_PANEL : GEMM_CHOL_COL;
       if ((rc = gemm(ga, J - 1 - j))) return rc;
       ++launches;
+      if (right_looking) {
+        ga.mode = GEMM_CHOL_TRAIL;
+        if ((rc = gemm(ga, (J - 1 - j) * (J - j) / 2))) return rc;
+        ++launches;
+      }
     }
   }
   if (prof) cudaEventRecord(b->ev[2], st);
@@ -157,19 +170,19 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, cudaSt
 }
 
 // One stream group of an evaluation pass: list[off .. off+count), the first ngrad of them with gradient.
-struct Group { int off, count, ngrad; };
+struct Group { int off, count, ngrad; bool rl; };
 
 // Order the active GPs of a pass into stream groups inside list_host: the value+gradient GPs and the value-only GPs
 // are each dealt evenly over the groups (equal work per stream), gradient GPs first inside every group.
 static std::vector<Group> build_groups(gprb_batch* b, const std::vector<int32_t>& grad_gps, const std::vector<int32_t>& val_gps) {
   const int total = (int)(grad_gps.size() + val_gps.size());
-  const int S = (b->profiling || total < 8 || b->nstreams == 1) ? 1 : b->nstreams;
+  const int S = (b->profiling || total < 8 || total <= b->rl_max || b->nstreams == 1) ? 1 : b->nstreams;
   std::vector<Group> groups;
   int off = 0;
   for (int s = 0; s < S; ++s) {
     const int g0 = (int)((int64_t)grad_gps.size() * s / S), g1 = (int)((int64_t)grad_gps.size() * (s + 1) / S);
     const int v0 = (int)((int64_t)val_gps.size() * s / S), v1 = (int)((int64_t)val_gps.size() * (s + 1) / S);
-    Group g{off, (g1 - g0) + (v1 - v0), g1 - g0};
+    Group g{off, (g1 - g0) + (v1 - v0), g1 - g0, !b->profiling && total <= b->rl_max};
     for (int k = g0; k < g1; ++k) b->list_host[off++] = grad_gps[k];
     for (int k = v0; k < v1; ++k) b->list_host[off++] = val_gps[k];
     if (g.count > 0) groups.push_back(g);
@@ -184,7 +197,7 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
   if (groups.empty()) return 0;
   if (b->profiling) {
     const Group& g = groups[0];
-    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, b->stream[0], true))) return rc;
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.rl, b->stream[0], true))) return rc;
     GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
     float ms = 0.f;
     const int last = g.ngrad > 0 ? 5 : 3;
@@ -210,7 +223,7 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
   for (size_t s = 0; s < groups.size(); ++s) {
     const Group& g = groups[s];
     if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(b->stream[s], b->join[0], 0));
-    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, b->stream[s], false))) return rc;
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.rl, b->stream[s], false))) return rc;
     if (s > 0) {
       GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
       GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
@@ -521,6 +534,8 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
       break;
     }
     b->nstreams = 4;
+    b->rl_max = 24;
+    if (const char* ev = getenv("GPRB200_RL_MAX")) b->rl_max = atoi(ev);
     if (const char* ev = getenv("GPRB200_STREAMS")) b->nstreams = std::max(1, std::min(MAX_STREAMS, atoi(ev)));
     for (int s = 0; s < MAX_STREAMS && !rc; ++s) {
       if ((e = cudaStreamCreateWithFlags(&b->stream[s], cudaStreamNonBlocking)) != cudaSuccess ||

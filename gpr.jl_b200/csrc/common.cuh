@@ -99,6 +99,7 @@ struct gprb_batch {
   int64_t stage_doubles = 0;
   cudaStream_t stream[gprb::MAX_STREAMS] = {};
   int nstreams = 1;
+  int rl_max = 24;                // passes with at most this many GPs use the right-looking (low-latency) factorisation
   cudaEvent_t ev[8] = {};
   cudaEvent_t join[gprb::MAX_STREAMS] = {};
   bool profiling = false;

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_assemble(AssembleArgs g) {
         v[e] = kf;
       }
       *reinterpret_cast<double2*>(A + r + (int64_t)c * g.npad) = make_double2(v[0], v[1]);
+      if (g.A2) *reinterpret_cast<double2*>(g.A2 + (int64_t)gp * g.mat_stride + r + (int64_t)c * g.npad) = make_double2(v[0], v[1]);
     }
   }
 }
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(GA_THREADS, 2) k_assemble_gram(AssembleArgs g)
     if (rr == c) kf = sf2 + diag_add;            // r2 is exactly zero on the diagonal
     if (rr >= n || c >= n) kf = (rr == c) ? 1.0 : 0.0;
     A[rr + (int64_t)c * g.npad] = kf;
+    if (g.A2) g.A2[(int64_t)gp * g.mat_stride + rr + (int64_t)c * g.npad] = kf;
   }
 }
 

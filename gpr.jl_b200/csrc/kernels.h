@@ -5,7 +5,8 @@
 
 namespace gprb {
 
-enum { GEMM_CHOL_DIAG = 0, GEMM_CHOL_COL = 1, GEMM_TRTRI_ROW = 2, GEMM_LAUUM = 3, GEMM_FWD_ROW = 4 };
+enum { GEMM_CHOL_DIAG = 0, GEMM_CHOL_COL = 1, GEMM_TRTRI_ROW = 2, GEMM_LAUUM = 3, GEMM_FWD_ROW = 4,
+       GEMM_CHOL_PANEL = 5, GEMM_CHOL_TRAIL = 6 };  // right-looking Cholesky for small batches (latency-bound chains)
 
 struct GemmArgs {
   const double* Lm;     // operand matrices [B][npad*npad]
@@ -35,6 +36,7 @@ struct AssembleArgs {
   const double* theta;      // [B][P]
   const double* jitter;     // [B]
   double* A;                // [B][npad*npad]
+  double* A2 = nullptr;     // optional second copy of the lower tiles (the right-looking factorisation works in place in Lm)
   int32_t* fail;            // [B] reset here: 0, or -2 for non-finite theta
   const int32_t* list;
   int64_t mat_stride;

@@ -18,6 +18,10 @@
 //   CHOL_COL   L(i,j)   = [K(i,j) - sum_{k<j} L(i,k) L(j,k)^T] * inv(L_jj)^T      -> Lm(i,j)   i > j = step
 //   TRTRI_ROW  W(i,j)   = -inv(L_ii) * sum_{k=j}^{i-1} L(i,k) W(k,j)   stored as V(j,i) = W(i,j)^T, i = step
 //   LAUUM      Kinv(i,j) = sum_{k>=i} V(i,k) V(j,k)^T  (i >= j)  -> upper tile (j,i) of A (un-transposed) / KinvD(i)
+//   CHOL_PANEL L(i,j)   = S(i,j) * inv(L_jj)^T                       in place in Lm, i > j = step      } right-looking
+//   CHOL_TRAIL S(i,k)  -= L(i,j) L(k,j)^T   for all j < k <= i          in place in Lm, j = step          } variant
+//              (small batches: 3 short launches per block column instead of serial k-loops that grow with the column
+//               index - the dependent chain of one factorisation drops from ~4.7 ms to ~1.8 ms at n = 2000)
 //   FWD_ROW    T(i,:)   = inv(L_ii) * [T(i,:) - sum_{k<i} L(i,k) T(k,:)]   in place in the right-hand-side block
 //              (blocked forward substitution L^-1 K* of the predictive variance, PDMats whiten!), i = step
 // where V = L^-T lives in the strictly-upper tiles of Lm and its diagonal blocks in DinvT.
@@ -67,6 +71,13 @@ __device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int b
     tc.i = step + 1 + bx; tc.j = step; tc.kb0 = 0; tc.kb1 = step; tc.use_cin = true; tc.post = 1; tc.rblk = step;
   } else if (mode == GEMM_TRTRI_ROW) {
     tc.i = step; tc.j = bx; tc.kb0 = bx; tc.kb1 = step; tc.b_diag_kb = bx; tc.post = 2; tc.rblk = step;
+  } else if (mode == GEMM_CHOL_PANEL) {
+    tc.i = step + 1 + bx; tc.j = step; tc.kb0 = 0; tc.kb1 = 0; tc.use_cin = true; tc.post = 1; tc.rblk = step;
+  } else if (mode == GEMM_CHOL_TRAIL) {  // bx enumerates the lower tiles of the trailing submatrix, row by row
+    int ii = (int)((__fsqrt_rn(8.0f * bx + 1.0f) - 1.0f) * 0.5f);
+    while ((ii + 1) * (ii + 2) / 2 <= bx) ++ii;
+    while (ii * (ii + 1) / 2 > bx) --ii;
+    tc.i = step + 1 + ii; tc.j = step + 1 + (bx - ii * (ii + 1) / 2); tc.kb0 = step; tc.kb1 = step + 1; tc.use_cin = true;
   } else if (mode == GEMM_FWD_ROW) {
     tc.i = step; tc.j = bx; tc.kb0 = 0; tc.kb1 = step; tc.use_cin = true; tc.post = 2; tc.rblk = step;
   } else {  // GEMM_LAUUM: bx enumerates (i, j), j <= i, row by row => longest k-range first
@@ -187,7 +198,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
 #endif
   int npred = 0;
   if (g.mode == GEMM_LAUUM) npred = min(nchunks, NB / KT);
-  else if (!RAGGED && g.mode == GEMM_CHOL_DIAG) npred = nchunks;
+  else if (!RAGGED && (g.mode == GEMM_CHOL_DIAG || (g.mode == GEMM_CHOL_TRAIL && tc.i == tc.j))) npred = nchunks;
   else if (!RAGGED && g.mode == GEMM_TRTRI_ROW) npred = NB / KT;
   const int diag_off = 4 * wn - 8 * wm;  // CHOL_DIAG: block (mi, ni) touches the lower triangle iff mi >= ni + diag_off
   const int sel_plain = sel_rows(mi_valid);

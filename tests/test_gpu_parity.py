@@ -284,6 +284,35 @@ def test_active_mask(gprb):
             assert rel(batch.alpha(b), oracle_all([tr], [thetas])[b]["state"]["alpha"]) <= 1e-8  # state kept
 
 
+@pytest.mark.parametrize("rl_max", ["0", "100000"])
+def test_left_and_right_looking_factorisations(gprb, rl_max, monkeypatch):
+    """Both Cholesky schedules (left-looking for throughput, right-looking for small latency-bound passes) on the same
+    ragged input: forced through GPRB200_RL_MAX, which is read when the batch is created."""
+    from gpr_jl_b200 import data
+    monkeypatch.setenv("GPRB200_RL_MAX", rl_max)
+    trials = [data.make_trial("CP", 300, seed=500 + t, n_test=3) for t in range(3)]
+    thetas = []
+    for tr in trials:
+        th = data.theta0("CP", tr["X"])
+        th[1:-1] -= 1.0
+        thetas.append(np.tile(th, (4, 1)) + 0.05 * np.random.default_rng(7).standard_normal((4, th.size)))
+    batch = build_batch(gprb, trials, thetas)
+    mll, grad, info = batch.eval(grad=True)
+    mu, var = batch.predict_y(trials[0]["Xtest"])
+    for b, r in enumerate(oracle_all(trials, thetas)):
+        assert info[b] == 0
+        assert abs(mll[b] - r["mll"]) <= 1e-8 * abs(r["mll"])
+        assert rel(grad[b], r["grad"]) <= 1e-8
+        assert rel(batch.chol_U(b), np.triu(r["state"]["U"])) <= 1e-10
+        assert rel(batch.Kinv(b), r["state"]["Kinv"]) <= 1e-8
+        X = np.ascontiguousarray(trials[b // 4]["X"].T)
+        m_o, v_o = go.predict(X, thetas[b // 4][b % 4], r["state"], np.ascontiguousarray(trials[0]["Xtest"].T))
+        assert rel(mu[b], m_o) <= 1e-9
+        np.testing.assert_allclose(var[b], v_o, rtol=1e-9, atol=1e-13)
+    mll2, _, _ = batch.eval(grad=False)
+    np.testing.assert_allclose(mll2, mll, rtol=1e-13)
+
+
 def test_mixed_value_and_gradient_pass(gprb):
     """gprb_eval_mixed (what the optimiser issues every round): value-only, value+gradient and skipped GPs in one pass."""
     from gpr_jl_b200 import data
