@@ -70,14 +70,14 @@ def test_eval_parity_well_conditioned(gprb, system, n):
     assert g2 is None and np.array_equal(mll, mll2)
 
 
-@pytest.mark.parametrize("n,d", [(2, 13), (4, 26), (8, 3), (16, 2), (50, 5), (129, 4)])
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 13), (4, 26), (8, 3), (16, 2), (50, 5), (129, 4), (40, 62)])
 def test_tiny_n_and_minimal_coordinate_d(gprb, n, d):
     """The reference sweeps n = 2, 4, 8 ... (examples/noise.jl:64, hyperparameter.jl:50) and its minimal-coordinate
     experiments use d = 2..6 (examples/minimal_coordinates/*); both go through the same boundary."""
     rng = np.random.default_rng(1000 * n + d)
     X = np.asfortranarray(rng.standard_normal((d, n)))
     Y = np.stack([np.sin(X[0]) + 0.05 * rng.standard_normal(n), X[d - 1] ** 2])
-    th = np.concatenate([[-1.0], np.log(np.full(d, 1.5)), [0.3]])
+    th = np.concatenate([[-1.0], np.log(np.full(d, 1.5 * np.sqrt(d))), [0.3]])  # length-scale grows with sqrt(d): K stays informative
     tr = {"X": X, "Y": Y}
     thetas = [np.tile(th, (2, 1)) + 0.05 * rng.standard_normal((2, d + 2))]
     batch = build_batch(gprb, [tr], thetas)
