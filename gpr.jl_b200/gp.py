@@ -306,14 +306,22 @@ class GPBatch:
         self.lib.check(self.lib.dll.gprb_batch_create(self.ctx.handle, self.B, ds_handles, _d(ymm), kind, C.byref(h)))
         self.handle = h
 
+    def close(self):
+        """Free the device memory of the batch and its datasets now (GPE <-> GPBatch reference cycles otherwise keep it
+        alive until the garbage collector runs - tens of GB at the benchmark sizes)."""
+        if getattr(self, "handle", None):
+            self.lib.dll.gprb_batch_destroy(self.handle)
+            self.handle = None
+        for h in getattr(self, "_ds", {}).values():
+            self.lib.dll.gprb_dataset_destroy(h)
+        self._ds = {}
+        for g in getattr(self, "gps", []):
+            if g._batch is self:
+                g._batch, g._slot = None, -1
+
     def __del__(self):
         try:
-            if getattr(self, "handle", None):
-                self.lib.dll.gprb_batch_destroy(self.handle)
-                self.handle = None
-            for h in getattr(self, "_ds", {}).values():
-                self.lib.dll.gprb_dataset_destroy(h)
-            self._ds = {}
+            self.close()
         except Exception:
             pass
 

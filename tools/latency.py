@@ -36,6 +36,7 @@ for system, B in (("CP", 1), ("CP", 4), ("FB", 12)):
     rows.append({"system": system, "B": B, "n": 2000, "d": tr["X"].shape[0], "eval_grad_ms": t_g, "eval_value_ms": t_v,
                  "predict_1col_meanvar_ms": t_p1, "predict_1col_mean_ms": t_pm})
     print(json.dumps(rows[-1]), flush=True)
+    batch.close()
     del batch
 if len(sys.argv) > 1:
     json.dump(rows, open(sys.argv[1], "w"), indent=1)

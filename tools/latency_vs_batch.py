@@ -17,4 +17,5 @@ for B in (4, 8, 20, 48, 100):
         for _ in range(reps): fn()
         return (time.perf_counter() - t0) / reps * 1e3
     print(json.dumps({"streams": os.environ.get("GPRB200_STREAMS", "4"), "B": B, "value_ms": timeit(lambda: batch.eval(grad=False)), "grad_ms": timeit(lambda: batch.eval(grad=True))}), flush=True)
+    batch.close()
     del batch

@@ -36,12 +36,13 @@ def main():
     ap.add_argument("--quick", action="store_true", help="n <= 2048 only")
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle (one evaluation per point, n <= 2048)")
     ap.add_argument("--gb", type=float, default=8.0, help="target HBM footprint per point")
+    ap.add_argument("--nmin", type=int, default=0, help="skip sizes below this n")
     a = ap.parse_args()
     import torch
     import gpr_jl_b200 as G
     peak = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAKS.json")))["dgemm_tflops_sustained"]
     dev = torch.device("cuda", 0)
-    ns = [256, 512, 1024, 2048] + ([] if a.quick else [4096, 8192])
+    ns = [n for n in [256, 512, 1024, 2048] + ([] if a.quick else [4096, 8192]) if n >= a.nmin]
     rows = []
     for n in ns:
         for d in (13, 26, 39, 52):
@@ -101,6 +102,7 @@ def main():
                 row["cpu_threads"] = os.cpu_count()
             rows.append(row)
             print(json.dumps(row), flush=True)
+            batch.close()
             del batch, gps
     if a.out:
         json.dump({"fp64_peak_tflops": peak, "peak_source": "profiles/FP64_PEAKS.json cuBLAS DGEMM 8192^3 sustained",
