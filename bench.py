@@ -232,6 +232,20 @@ def main():
     info_ok = int((info_dev >= 0).sum().item())
     value = world * B * args.steps / (ms_total * 1e-3)
 
+    # ---- value-only evaluations (the optimiser's line-search trials: assembly + Cholesky + solve), device resident
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    batch.eval_device(th_dev[0].data_ptr(), mll_dev.data_ptr(), None, info_dev.data_ptr(), stream.cuda_stream)
+    barrier()
+    v0.record(stream)
+    for k in range(args.steps):
+        batch.eval_device(th_dev[args.warmup + k].data_ptr(), mll_dev.data_ptr(), None, info_dev.data_ptr(), stream.cuda_stream)
+    v1.record(stream)
+    barrier()
+    msv = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(msv, op=dist.ReduceOp.MAX)
+    value_only = world * B * args.steps / (float(msv.item()) * 1e-3)
+
     # ---- e2e: public API with host buffers; X, y, theta go up and mll, grad come back every step
     # host inputs live in page-locked memory (the copies inside the timed region are then real async DMA transfers)
     X_pin = torch.empty((T, n, d), dtype=torch.float64).pin_memory().numpy()
@@ -319,7 +333,9 @@ def main():
                        "l2": f"working set {2 * B * batch.n * batch.n * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "info_ok": info_ok, "parallelism": f"trial-sharded x{world}, per-step NCCL all-gather of results"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
+            "value_only": {"value": value_only, "unit": "evals/s", "frac_fp64_peak": (n ** 3 / 3 + 1.5 * d * n ** 2 + 2 * n ** 2) * value_only / world / 1e12 / peak,
+                           "note": "logML without gradient (line-search trials of optimize!): assembly + Cholesky + solve"}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if pred:
