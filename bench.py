@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--trials", type=int, default=TRIALS, help="trial datasets per GPU (default: the full 100)")
-    ap.add_argument("--n", type=int, default=N_TRAIN)
+    ap.add_argument("--n-train", dest="n", type=int, default=N_TRAIN)  # not "--n": torchrun would read it as its own abbreviation
     ap.add_argument("--system", default=SYSTEM, choices=["P1", "P2", "CP", "FB"],
                     help="BASELINE config family (default CP, the one the metric is quoted on); FB = d=52, 12 GPs per trial")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

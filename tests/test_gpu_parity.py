@@ -313,6 +313,27 @@ def test_left_and_right_looking_factorisations(gprb, rl_max, monkeypatch):
     np.testing.assert_allclose(mll2, mll, rtol=1e-13)
 
 
+def test_results_do_not_depend_on_batch_composition(gprb):
+    """Sharding invariance (multi-GPU row): a GP's results are bit-identical whether it is evaluated
+    alone, in a small pass (right-looking schedule, one stream) or among 40 GPs (left-looking schedule, four streams) -
+    which is why any trial -> rank partition reproduces the single-GPU run exactly."""
+    from gpr_jl_b200 import data
+    trials = data.make_config("CP", trials=10, n=200)
+    thetas = [np.tile(data.theta0("CP", tr["X"]), (4, 1)) + 0.1 * np.random.default_rng(t).standard_normal((4, 28))
+              for t, tr in enumerate(trials)]
+    big = build_batch(gprb, trials, thetas)                 # 40 GPs
+    mll_b, grad_b, _ = big.eval(grad=True)
+    mu_b, var_b = big.predict_y(trials[0]["X"][:, :5])
+    small = build_batch(gprb, trials[3:4], thetas[3:4])     # the 4 GPs of trial 3
+    mll_s, grad_s, _ = small.eval(grad=True)
+    mu_s, var_s = small.predict_y(trials[0]["X"][:, :5])
+    assert np.array_equal(mll_s, mll_b[12:16]) and np.array_equal(grad_s, grad_b[12:16])
+    assert np.array_equal(mu_s, mu_b[12:16]) and np.array_equal(var_s, var_b[12:16])
+    one = build_batch(gprb, [{"X": trials[3]["X"], "Y": trials[3]["Y"][2:3]}], [thetas[3][2:3]])
+    mll_1, grad_1, _ = one.eval(grad=True)
+    assert mll_1[0] == mll_b[14] and np.array_equal(grad_1[0], grad_b[14])
+
+
 def test_mixed_value_and_gradient_pass(gprb):
     """gprb_eval_mixed (what the optimiser issues every round): value-only, value+gradient and skipped GPs in one pass."""
     from gpr_jl_b200 import data
