@@ -11,6 +11,10 @@ CMD="python bench.py --steps 1 --warmup 1 --trials 12 --cpu-seconds 0"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "launch list rc=$?"
+FULL="python bench.py --steps 1 --warmup 3 --cpu-seconds 0 --no-predict"   # 1b. the same list at the full bench configuration
+$FULL > gpurun_out/${TAG}_full_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_B400.csv $FULL > gpurun_out/${TAG}_full_ncu.log 2>&1
+echo "full launch list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_tile_gemm -s 44 -c 3 -f -o gpurun_out/${TAG}_gemm $CMD > gpurun_out/${TAG}_ncu_gemm.log 2>&1
 echo "gemm capture rc=$?"

@@ -34,6 +34,27 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"| {k} | {v[0]} | {v[1]:.3f} | {v[1] / tot:.3f} |")
 shutil.copy(os.path.join(go, f"{tag}_launches.csv"), os.path.join(pr, f"{tag}_launches.csv"))
 
+full = os.path.join(go, f"{tag}_launches_B400.csv")
+if os.path.exists(full):  # launch list of the FULL bench configuration (tools/profile.sh step 1b)
+    rows = [r for r in csv.reader(open(full)) if len(r) > 5]
+    agg = collections.OrderedDict()
+    for r in rows:
+        if r[0] == "ID":
+            continue
+        v = float(r[mv].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(r[mu], 1e-6)
+        name = r[kn].split("(")[0].replace("void ", "").replace("gprb::", "")
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values())
+    lines += ["", "## Launch list at the full bench configuration (`bench.py --steps 1 --warmup 3 --no-predict`: B=400 GPs, n=2000, d=26)", "",
+              "The share of `k_tile_gemm` here is to be compared with the CUDA-event stage times `bench.py` reports "
+              "(`roofline.stage_ms`: gemm / total).", "", "| kernel | launches | total ms | share |", "|---|---|---|---|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        if v[1] / tot >= 0.0005:
+            lines.append(f"| {k} | {v[0]} | {v[1]:.3f} | {v[1] / tot:.3f} |")
+    shutil.copy(full, os.path.join(pr, f"{tag}_launches_B400.csv"))
+
 WANT = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
         ("launch__registers_per_thread", "regs/thread"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
         ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
