@@ -1,13 +1,14 @@
 // K1 covariance assembly and K5 fused log-marginal-likelihood gradient.
 //
-// Both are pairwise kernels over 128x128 tiles of sample pairs.  The two d x 128 input tiles are staged
-// by the TMA engine (one 1 KB bulk copy per input dimension from the dataset's transposed copy Xt[d][npad],
-// completion on an mbarrier); each thread then owns an 8x8 block of pairs in registers.
-// Distances follow the reference's direct-difference form  r2 = sum_p w_p (x_ip - x_jp)^2  (never the
-// |x|^2 + |x'|^2 - 2 x.x' expansion, which loses 1e-12 parity on near-duplicate trajectory samples).
-// The gradient kernel never materialises Q = alpha alpha' - K^-1 or dK/dtheta:
-//     g_noise = s_n^2 tr(Q),  g_ll_p = 1/2 w_p sum_ij Q_ij g(r_ij) (x_ip - x_jp)^2,  g_lsigma = sum_ij Q_ij K_f,ij
-// Per-tile partial sums are written to HBM and reduced in a fixed order by a second kernel (deterministic).
+// Pairwise kernels over tiles of sample pairs.  The d x 128 input tiles are staged by the TMA engine (one bulk
+// copy per input dimension from the dataset's transposed copy Xt[d][npad], completion on an mbarrier).
+//   k_assemble_gram  (default) the cross term of r2 = |z_i|^2 + |z_j|^2 - 2 z_i.z_j on DMMA, with an exact
+//                    direct-difference path for the pairs where the expansion would lose the 1e-12 parity
+//   k_assemble       the all-direct-difference kernel  r2 = sum_p w_p (x_ip - x_jp)^2  (the reference's form)
+//   k_grad_tiles     the gradient, always by direct differences; it never materialises Q = alpha alpha' - K^-1 or
+//                    dK/dtheta:  g_noise = s_n^2 tr(Q),  g_ll_p = 1/2 w_p sum_ij Q_ij g(r_ij) (x_ip - x_jp)^2,
+//                    g_lsigma = sum_ij Q_ij K_f,ij
+// Per-block partial sums go to HBM and are reduced in a fixed order by a second kernel (deterministic).
 #include <stdlib.h>
 
 #include <algorithm>
