@@ -20,7 +20,8 @@ restatement against reference outputs.  What this file does instead: it
 restates the *published algorithm* of those package versions in the reference's
 operation order, using the same LAPACK family (scipy -> OpenBLAS), and is itself
 checked by finite differences and an extended-precision arbiter
-(``longdouble_eval``) in ``tests/test_oracle.py``.
+(``longdouble_eval``) in ``tests/test_oracle.py``, and against scikit-learn's independent
+GaussianProcessRegressor in ``tests/test_oracle_vs_sklearn.py`` (agreement ~1e-14).
 
 Reference call sites that define the boundary this oracle restates:
   * examples/maximal_coordinates/CPnoise.jl:38-41  SEArd(log.(l), log(sf)); GP(X, y, mean, kernel); optimize!
