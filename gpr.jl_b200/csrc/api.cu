@@ -698,10 +698,25 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
         GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->KinvD, nullptr, b->npad * b->npad, (int64_t)J * NB * NB,
                     (int)b->npad, J, 0, GEMM_FWD_ROW, nv};
         ga.Tm = b->pT; ga.t_stride = b->npad * PT; ga.ldt = PT;
-        for (int i = 0; i < J; ++i) {
-          ga.step = i;
-          if ((rc = launch_tile_gemm(ga, 1, B, st))) return rc;
-          b->ctx->launches++;
+        ga.ncols = ta.mc;
+        // the GPs are dealt over the stream groups: the dependent chain of J launches of one group fills the wave
+        // tails of the others (B tiles per launch are not a multiple of the SM count)
+        const int S = (B >= 8 * b->nstreams) ? b->nstreams : 1;
+        if (S > 1) GPRB_CUDA(cudaEventRecord(b->join[0], st));
+        for (int s = 0; s < S; ++s) {
+          const int g0 = (int)((int64_t)B * s / S), g1 = (int)((int64_t)B * (s + 1) / S);
+          cudaStream_t ss = b->stream[s];
+          if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(ss, b->join[0], 0));
+          ga.gp_off = g0;
+          for (int i = 0; i < J; ++i) {
+            ga.step = i;
+            if ((rc = launch_tile_gemm(ga, 1, g1 - g0, ss))) return rc;
+            b->ctx->launches++;
+          }
+          if (s > 0) {
+            GPRB_CUDA(cudaEventRecord(b->join[s], ss));
+            GPRB_CUDA(cudaStreamWaitEvent(st, b->join[s], 0));
+          }
         }
       }
       if ((rc = launch_predict_finish(ta, B, st))) return rc;

@@ -24,6 +24,8 @@ struct GemmArgs {
   double* Tm = nullptr;
   int64_t t_stride = 0;
   int ldt = 0;
+  int ncols = 128;      // valid test columns of the block (< 128: compact warp layout skips the padding columns)
+  int gp_off = 0;       // first GP of this launch when `list` is null (stream groups of gprb_predict)
   const int32_t* fail = nullptr;     // [B] per-GP failure flag: tiles of a GP whose factorisation already broke down exit at once
   unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)
 };

@@ -90,7 +90,7 @@ __device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int b
   return tc;
 }
 
-enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_MI4, SEL_MI6, SEL_NI2, SEL_TRI0, SEL_TRI4 };
+enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_MI4, SEL_MI6, SEL_NI1, SEL_NI2, SEL_NI3, SEL_TRI0, SEL_TRI4 };
 
 // One k-chunk (KT = 16) of a warp's 64x32 register tile restricted, at compile time, to the 8x8 blocks
 // (mi, ni) with mi < MI_LIM, ni < NI_LIM and mi >= ni + OFF: straight-line unpredicated DMMAs.
@@ -122,13 +122,18 @@ __device__ __forceinline__ void chunk_dispatch(int sel, double (&acc)[8][4][2], 
     case SEL_MI2: chunk_mma<2, 4, -64>(acc, ap, bp); break;
     case SEL_MI4: chunk_mma<4, 4, -64>(acc, ap, bp); break;
     case SEL_MI6: chunk_mma<6, 4, -64>(acc, ap, bp); break;
+    case SEL_NI1: chunk_mma<8, 1, -64>(acc, ap, bp); break;
     case SEL_NI2: chunk_mma<8, 2, -64>(acc, ap, bp); break;
+    case SEL_NI3: chunk_mma<8, 3, -64>(acc, ap, bp); break;
     case SEL_TRI0: chunk_mma<8, 4, 0>(acc, ap, bp); break;
     case SEL_TRI4: chunk_mma<8, 4, 4>(acc, ap, bp); break;
     default: chunk_mma<8, 4, -64>(acc, ap, bp); break;
   }
 }
 
+__device__ __forceinline__ int sel_cols(int ni_lim) {
+  return ni_lim <= 0 ? SEL_SKIP : ni_lim == 1 ? SEL_NI1 : ni_lim == 2 ? SEL_NI2 : ni_lim == 3 ? SEL_NI3 : SEL_FULL;
+}
 __device__ __forceinline__ int sel_rows(int mi_lim) {  // mi_lim is even (n is padded to 16-row chunks)
   return mi_lim <= 0 ? SEL_SKIP : mi_lim == 2 ? SEL_MI2 : mi_lim == 4 ? SEL_MI4 : mi_lim == 6 ? SEL_MI6 : SEL_FULL;
 }
@@ -148,15 +153,27 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   const int wn = h ? (3 - s4) : s4;    // ... with column groups {s, 3-s} (triangular post-multiply skip balances)
   const int mi_valid = RAGGED ? min(8, max(0, (rows_valid - wm * 64 + 7) / 8)) : 8;
   const int gq = lane >> 2, t = lane & 3;
+  const bool fwd = g.mode == GEMM_FWD_ROW;
+  // Column layout of the warp grid.  Default: column group wn owns the four 8-column blocks at 32 wn.  FWD_ROW tiles
+  // whose right-hand-side block has fewer than 128 valid test columns (the reference predicts m = 100 test states per
+  // step) use a compact layout: the nblk = ceil(ncols / 8) valid 8-column blocks are dealt over the four column groups
+  // (extras to groups 0, 1, 3 so the SMSP pairs {0,3} / {1,2} stay balanced) and every warp runs the chunk body
+  // specialised to its own block count - the padding columns are neither multiplied nor loaded nor stored.
+  int cbase = wn * 32, ni_lim = 4;
+  if (fwd && !RAGGED && g.ncols < NB) {
+    const int nblk = (g.ncols + 7) >> 3, q = nblk >> 2, rem = nblk & 3;
+    const int w0 = q + (rem >= 1), w1 = q + (rem >= 2), w2 = q, w3 = q + (rem >= 3);
+    ni_lim = wn == 0 ? w0 : wn == 1 ? w1 : wn == 2 ? w2 : w3;
+    cbase = 8 * (wn == 0 ? 0 : wn == 1 ? w0 : wn == 2 ? w0 + w1 : w0 + w1 + w2);
+  }
   const int row0 = wm * 64 + gq;  // + mi*8
-  const int col0 = wn * 32 + gq;  // + ni*8  (operand row index of B)
+  const int col0 = cbase + gq;    // + ni*8  (operand row index of B)
 
   // The accumulators start at -Cin (Cholesky tiles: K(i,j); FWD_ROW: the right-hand-side block), loaded straight
   // into the accumulator registers while the first operand chunks are still in flight: the 64 global loads per
   // thread need no extra registers and their latency hides behind the pipeline fill.  After the k-loop
   // acc = sum - Cin = -(Cin - sum); the sign is folded into the stores below.
   const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * NB;
-  const bool fwd = g.mode == GEMM_FWD_ROW;
   double acc[8][4][2];
   if (fwd) {
     const double* Tin = g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt;
@@ -164,9 +181,9 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        const int r = wm * 64 + mi * 8 + gq, cc = cbase + ni * 8 + 2 * t;
         double2 v = make_double2(0.0, 0.0);
-        if (!RAGGED || mi < mi_valid) v = *reinterpret_cast<const double2*>(Tin + cc + (int64_t)r * g.ldt);
+        if ((!RAGGED || mi < mi_valid) && ni < ni_lim) v = *reinterpret_cast<const double2*>(Tin + cc + (int64_t)r * g.ldt);
         acc[mi][ni][0] = -v.x;
         acc[mi][ni][1] = -v.y;
       }
@@ -201,7 +218,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   else if (!RAGGED && (g.mode == GEMM_CHOL_DIAG || (g.mode == GEMM_CHOL_TRAIL && tc.i == tc.j))) npred = nchunks;
   else if (!RAGGED && g.mode == GEMM_TRTRI_ROW) npred = NB / KT;
   const int diag_off = 4 * wn - 8 * wm;  // CHOL_DIAG: block (mi, ni) touches the lower triangle iff mi >= ni + diag_off
-  const int sel_plain = sel_rows(mi_valid);
+  const int sel_plain = ni_lim < 4 ? sel_cols(ni_lim) : sel_rows(mi_valid);  // (the compact layout is never ragged)
   {
     int stage = 0; uint32_t phase = 0;
     for (int c = 0; c < nchunks; ++c) {
@@ -276,9 +293,9 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        const int r = wm * 64 + mi * 8 + gq, cc = cbase + ni * 8 + 2 * t;
         const bool ok = !RAGGED || mi < mi_valid;
-        *reinterpret_cast<double2*>(&Ts[r * LDS_T + cc]) = ok ? make_double2(acc[mi][ni][0], acc[mi][ni][1]) : make_double2(0.0, 0.0);
+        if (ni < ni_lim) *reinterpret_cast<double2*>(&Ts[r * LDS_T + cc]) = ok ? make_double2(acc[mi][ni][0], acc[mi][ni][1]) : make_double2(0.0, 0.0);
       }
   }
 #pragma unroll
@@ -321,8 +338,8 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        if (RAGGED && mi >= mi_valid) continue;
-        const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
+        if ((RAGGED && mi >= mi_valid) || ni >= ni_lim) continue;
+        const int r = wm * 64 + mi * 8 + gq, cc = cbase + ni * 8 + 2 * t;
         *reinterpret_cast<double2*>(&outp[cc + r * ldo]) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
       }
   }
@@ -341,7 +358,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
 
   GPRB_TL(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  const int gp = g.list ? g.list[blockIdx.y] : g.gp_off + blockIdx.y;
   // A GP whose factorisation already hit a non-positive pivot (make_posdef! will retry it with more jitter) skips the
   // rest of the failed attempt, like dpotrf stopping at the failing column.  The load overlaps the setup below.
   const int failed = g.fail ? g.fail[gp] : 0;
