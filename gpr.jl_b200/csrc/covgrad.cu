@@ -60,10 +60,11 @@ __device__ __forceinline__ void stage_inputs(const double* Xt, int npad, int d, 
   __syncthreads();
   if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(2 * d * NB * sizeof(double)));
   __syncthreads();
-  for (int p = threadIdx.x; p < 2 * d; p += blockDim.x) {
-    const int q = p < d ? p : p - d;
-    const int blk = p < d ? i : j;
-    bulk_g2s((p < d ? Xi : Xj) + q * NB, Xt + (int64_t)q * npad + (int64_t)blk * NB, NB * sizeof(double), bar);
+  const int uwarp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform operands: see k_assemble_gram
+  if (uwarp < 2 && (threadIdx.x & 31) == 0) {
+    double* dst = uwarp ? Xj : Xi;
+    const double* src = Xt + (int64_t)(uwarp ? j : i) * NB;
+    for (int q = 0; q < d; ++q) bulk_g2s(dst + q * NB, src + (int64_t)q * npad, NB * sizeof(double), bar);
   }
   mbar_wait(bar, 0);
 }
@@ -190,9 +191,14 @@ __global__ void __launch_bounds__(GA_THREADS, 2) k_assemble_gram(AssembleArgs g)
   __syncthreads();
   if (tid == 0) mbar_expect_tx(bar, (uint32_t)(d * (NB + GA_CW) * sizeof(double)));
   __syncthreads();
-  for (int k = tid; k < 2 * d; k += GA_THREADS) {
-    if (k < d) bulk_g2s(Zi + k * LDS_T, Xt + (int64_t)k * g.npad + (int64_t)ti * NB, NB * sizeof(double), bar);
-    else bulk_g2s(Zj + (k - d) * GA_LDJ, Xt + (int64_t)(k - d) * g.npad + c0, GA_CW * sizeof(double), bar);
+  {  // lane 0 of warps 0-3 issues the copies with warp-uniform operands (per-lane addresses would serialise the
+     // uniform-datapath UBLKCP through an ELECT / R2UR.BROADCAST loop over the lanes): warps 0, 1 the row tile, 2, 3 the column tile
+    const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+    if (uwarp < 4 && lane == 0) {
+      const int half_d = (d + 1) >> 1, k0 = (uwarp & 1) * half_d, k1 = (uwarp & 1) ? d : half_d;
+      if (uwarp < 2) for (int k = k0; k < k1; ++k) bulk_g2s(Zi + k * LDS_T, Xt + (int64_t)k * g.npad + (int64_t)ti * NB, NB * sizeof(double), bar);
+      else for (int k = k0; k < k1; ++k) bulk_g2s(Zj + k * GA_LDJ, Xt + (int64_t)k * g.npad + c0, GA_CW * sizeof(double), bar);
+    }
   }
   if (tid < d) {
     const double wp = exp(-2.0 * th[1 + tid]);  // SEArd stores il2 = exp(-2 ll)
@@ -303,14 +309,19 @@ static_assert(GRAD_CW == 32, "thread mapping below assumes 32-column blocks");
 constexpr int GRAD_DH = 32;  // input dimensions resident at a time: d > 32 (FB: d = 52) streams its input tiles in two passes
                              // so that the CTA stays at ~105 KB of smem and two CTAs fit an SM for every d
 
-template <int KIND, bool MULTI>  // MULTI = false: d <= GRAD_DH, one resident pass (the common case compiles without the pass logic)
-__global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
+// LEAN (d <= 30, where the (d + 2) x 128 reduction buffer fits the K^-1 landing zone alone): the K block is not landed in
+// shared memory but prefetched into 32 registers per thread before the wait on the bulk copies - 66 KB per CTA, so THREE
+// CTAs share an SM and the FP64 phase of one always has the copies / reductions of two others to hide behind (with two
+// CTAs per SM the DFMA pipe sat at 56 %: a CTA spends longer outside its FP64 phase than inside).
+template <int KIND, bool MULTI, bool LEAN>  // MULTI = false: d <= GRAD_DH, one resident pass (the common case compiles without the pass logic)
+__global__ void __launch_bounds__(GRAD_THREADS, LEAN ? 3 : 2) k_grad_tiles(GradArgs g) {
+  static_assert(!(MULTI && LEAN), "the lean layout is single-pass");
   constexpr int CW = GRAD_CW, NT = GRAD_THREADS, NQ = NB / CW, DH = MULTI ? GRAD_DH : MAX_D + 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = g.d, dh = min(d, DH), npass = MULTI ? (d + DH - 1) / DH : 1;
   double* Ki = reinterpret_cast<double*>(smem_raw);  // [CW][NB] K^-1 block, column-major; reused as `red` afterwards
-  double* Kb = Ki + CW * NB;                          // [CW][NB] K block (SEArd only)
-  double* Xi = Kb + CW * NB;                          // [dh][NB]  input tile of the current pass
+  double* Kb = Ki + CW * NB;                          // [CW][NB] K block (SEArd only; absent in the lean layout)
+  double* Xi = LEAN ? Kb : Kb + CW * NB;              // [dh][NB]  input tile of the current pass
   double* Xj = Xi + dh * NB;                          // [dh][CW]
   double* w = Xj + dh * CW;                           // [MAX_D]
   uint64_t* bar = reinterpret_cast<uint64_t*>(w + MAX_D);
@@ -331,6 +342,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
   else { ldk = g.npad; Kinv = g.A + (int64_t)gp * g.mat_stride + (int64_t)tj * NB + ((int64_t)ti * NB + cbase) * ldk; }
   if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
+  const int uwarp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp index, provably warp-uniform
+  const bool lane0 = (threadIdx.x & 31) == 0;
   // Input tiles of pass q (dimensions q*DH ..): one bulk copy per dimension and tile.  `cur` = resident pass.
   uint32_t parity = 0;
   int cur = 0;
@@ -338,9 +351,14 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
     const int p0 = q * DH, pc = min(DH, d - p0);
     if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(pc * (NB + CW) * sizeof(double)) + extra_bytes);
     __syncthreads();
-    for (int k = threadIdx.x; k < 2 * pc; k += NT) {
-      if (k < pc) bulk_g2s(Xi + k * NB, Xt + (int64_t)(p0 + k) * g.npad + (int64_t)ti * NB, NB * sizeof(double), bar);
-      else bulk_g2s(Xj + (k - pc) * CW, Xt + (int64_t)(p0 + k - pc) * g.npad + (int64_t)tj * NB + cbase, CW * sizeof(double), bar);
+    // Copies are issued by lane 0 of a warp with warp-uniform operands (uwarp): with per-lane addresses the compiler
+    // serialises the uniform-datapath UBLKCP through an ELECT / R2UR.BROADCAST loop over the lanes (~90 cycles per copy).
+    if (uwarp == 2 && lane0) {
+      const double* src = Xt + (int64_t)p0 * g.npad + (int64_t)ti * NB;
+      for (int k = 0; k < pc; ++k) bulk_g2s(Xi + k * NB, src + (int64_t)k * g.npad, NB * sizeof(double), bar);
+    } else if (uwarp == 3 && lane0) {
+      const double* src = Xt + (int64_t)p0 * g.npad + (int64_t)tj * NB + cbase;
+      for (int k = 0; k < pc; ++k) bulk_g2s(Xj + k * CW, src + (int64_t)k * g.npad, CW * sizeof(double), bar);
     }
   };
   auto need_pass = [&](int q) {  // make pass q resident (no-op when it already is)
@@ -352,14 +370,32 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
     cur = q;
   };
   // first batch: 32 + 32 matrix columns and the input tiles of pass 0, all in flight at once
-  issue_x(0, (uint32_t)((REUSE_K ? 2 : 1) * CW * NB * sizeof(double)));
-  for (int k = threadIdx.x; k < 2 * CW; k += NT) {
-    if (k < CW) bulk_g2s(Ki + k * NB, Kinv + (int64_t)k * ldk, NB * sizeof(double), bar);
-    else if (REUSE_K) bulk_g2s(Kb + (k - CW) * NB, Kt + (int64_t)(k - CW) * g.npad, NB * sizeof(double), bar);
+  constexpr bool LAND_K = REUSE_K && !LEAN;
+  issue_x(0, (uint32_t)((LAND_K ? 2 : 1) * CW * NB * sizeof(double)));
+  if (LAND_K) {  // warp 0: K^-1 block, warp 1: K block
+    if (uwarp == 0 && lane0) {
+#pragma unroll 4
+      for (int k = 0; k < CW; ++k) bulk_g2s(Ki + k * NB, Kinv + (int64_t)k * ldk, NB * sizeof(double), bar);
+    } else if (uwarp == 1 && lane0) {
+#pragma unroll 4
+      for (int k = 0; k < CW; ++k) bulk_g2s(Kb + k * NB, Kt + (int64_t)k * g.npad, NB * sizeof(double), bar);
+    }
+  } else if (uwarp < 2 && lane0) {  // warps 0 and 1: one half of the K^-1 block each
+    const int k0 = uwarp * (CW / 2);
+#pragma unroll 4
+    for (int k = k0; k < k0 + CW / 2; ++k) bulk_g2s(Ki + k * NB, Kinv + (int64_t)k * ldk, NB * sizeof(double), bar);
   }
   if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
   const double sf2 = exp(2.0 * th[d + 1]);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double2 kreg[4][4];  // lean layout: this thread's 8 x 4 entries of the K block, in flight while the bulk copies land
+  if (LEAN && REUSE_K) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int a2 = 0; a2 < 4; ++a2)
+        kreg[b][a2] = *reinterpret_cast<const double2*>(Kt + (int64_t)(16 * (b >> 1) + 2 * ty + (b & 1)) * g.npad + loc8(2 * a2, tx));
+  }
   const double* alpha = g.alpha + (int64_t)gp * g.npad;
   const int n = g.n;
   double ar[8], ac[4];
@@ -415,7 +451,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 2) k_grad_tiles(GradArgs g) {
       const double kin[2] = {kv.x, kv.y};
       double kst[2] = {0.0, 0.0};
       if (REUSE_K) {
-        const double2 ks = *reinterpret_cast<const double2*>(Kb + cl * NB + rl);
+        const double2 ks = LEAN ? kreg[b][a >> 1] : *reinterpret_cast<const double2*>(Kb + cl * NB + rl);
         kst[0] = ks.x; kst[1] = ks.y;
       }
 #pragma unroll
@@ -521,8 +557,8 @@ __global__ void k_add_jitter(const double* theta, double* jitter, const int32_t*
   jitter[gp] += 1e-6 * mean_diag;
 }
 
-static size_t pw_smem(int d, bool grad) {
-  size_t doubles = grad ? (size_t)2 * GRAD_CW * NB + (size_t)std::min(d, GRAD_DH) * (NB + GRAD_CW) + MAX_D : (size_t)2 * d * NB + MAX_D;
+static size_t pw_smem(int d, bool grad, bool lean = false) {
+  size_t doubles = grad ? (size_t)(lean ? 1 : 2) * GRAD_CW * NB + (size_t)std::min(d, GRAD_DH) * (NB + GRAD_CW) + MAX_D : (size_t)2 * d * NB + MAX_D;
   return doubles * sizeof(double) + 16;
 }
 
@@ -571,17 +607,20 @@ int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream) {
 
 int launch_grad(const GradArgs& a, int count, cudaStream_t stream) {
   if (count <= 0) return 0;
-  const size_t smem = pw_smem(a.d, true);
+  // lean layout (three CTAs per SM) whenever the (d + 2) x 128 reduction buffer fits the K^-1 landing zone;
+  // GPRB200_GRAD_LEAN=0 forces the two-block layout (A/B comparisons)
+  static const bool allow_lean = [] { const char* e = getenv("GPRB200_GRAD_LEAN"); return !(e && e[0] == '0'); }();
+  const bool lean = allow_lean && (a.d + 2) * GRAD_THREADS <= GRAD_CW * NB;
+  const size_t smem = pw_smem(a.d, true, lean);
   dim3 grid(a.J * (a.J + 1) / 2 * (NB / GRAD_CW), count);
   int rc = 0;
-#define GPRB_GRAD_CASE(K)                                             \
-  if (a.d <= GRAD_DH) {                                               \
-    rc = set_smem(k_grad_tiles<K, false>, smem);                      \
-    if (!rc) k_grad_tiles<K, false><<<grid, GRAD_THREADS, smem, stream>>>(a); \
-  } else {                                                            \
-    rc = set_smem(k_grad_tiles<K, true>, smem);                       \
-    if (!rc) k_grad_tiles<K, true><<<grid, GRAD_THREADS, smem, stream>>>(a);  \
-  }
+#define GPRB_GRAD_LAUNCH(K, M, L)                                         \
+  rc = set_smem(k_grad_tiles<K, M, L>, smem);                             \
+  if (!rc) k_grad_tiles<K, M, L><<<grid, GRAD_THREADS, smem, stream>>>(a);
+#define GPRB_GRAD_CASE(K)                                                 \
+  if (lean) { GPRB_GRAD_LAUNCH(K, false, true) }                          \
+  else if (a.d <= GRAD_DH) { GPRB_GRAD_LAUNCH(K, false, false) }          \
+  else { GPRB_GRAD_LAUNCH(K, true, false) }
   switch (a.kind) {
     case GPRB_KERNEL_SE_ARD: GPRB_GRAD_CASE(0) break;
     case GPRB_KERNEL_MAT12_ARD: GPRB_GRAD_CASE(1) break;
@@ -589,6 +628,7 @@ int launch_grad(const GradArgs& a, int count, cudaStream_t stream) {
     default: GPRB_GRAD_CASE(3) break;
   }
 #undef GPRB_GRAD_CASE
+#undef GPRB_GRAD_LAUNCH
   if (rc) return rc;
   k_grad_reduce<<<count, 64, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();

@@ -159,8 +159,11 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
   __syncthreads();
   if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(d * NB * sizeof(double)));
   __syncthreads();
-  for (int p = threadIdx.x; p < d; p += PC_THREADS)
-    bulk_g2s(Xi + p * NB, Xt + (int64_t)p * g.npad + (int64_t)ib * NB, NB * sizeof(double), bar);
+  {  // lane 0 of warps 0-3 issues the copies with warp-uniform operands (per-lane addresses serialise the UBLKCP issue)
+    const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+    if (uwarp < 4 && lane == 0)
+      for (int p = uwarp; p < d; p += 4) bulk_g2s(Xi + p * NB, Xt + (int64_t)p * g.npad + (int64_t)ib * NB, NB * sizeof(double), bar);
+  }
   const double* Xstar = g.Xstar + (int64_t)gp * g.xstar_stride + (int64_t)g.s0 * d;
   for (int idx = threadIdx.x; idx < d * PT; idx += PC_THREADS) {
     const int s = idx / d, p = idx - s * d;  // consecutive threads walk one test column: coalesced global reads

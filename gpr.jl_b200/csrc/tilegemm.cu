@@ -392,11 +392,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
     auto issue_r = [&](int c) {  // chunk c of the post-multiplier -> rbuf[c & 1]
       const int buf = c % NRBUF;
       mbar_wait(&rempty[buf], ((c / NRBUF) & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(&rfull[buf], KT * NB * sizeof(double));
-      __syncwarp();
-      if (lane < KT) {
-        const double* src = Dinv + (int64_t)tc.rblk * NB * NB + (int64_t)(c * KT + lane) * NB;
-        bulk_g2s(rbuf + buf * RBUF_DOUBLES + lane * LDS_T, src, NB * sizeof(double), &rfull[buf]);
+      // one lane issues all the copies of a chunk with warp-uniform operands: per-lane addresses would make the
+      // compiler serialise the uniform-datapath UBLKCP through an ELECT / R2UR.BROADCAST loop (~90 cycles per copy)
+      if (lane == 0) {
+        mbar_expect_tx(&rfull[buf], KT * NB * sizeof(double));
+        const double* src = Dinv + (int64_t)tc.rblk * NB * NB + (int64_t)(c * KT) * NB;
+        double* dst = rbuf + buf * RBUF_DOUBLES;
+#pragma unroll
+        for (int r = 0; r < KT; ++r) bulk_g2s(dst + r * LDS_T, src + r * NB, NB * sizeof(double), &rfull[buf]);
       }
     };
     int issued = 0;  // main chunks issued so far; the post-multiplier prefetch follows the first ring fill
@@ -410,11 +413,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
       const int cend = (kb == g.J - 1) ? last_kb_chunks : NB / KT;
       for (int c = 0; c < cend; ++c) {
         mbar_wait(&empty[stage], phase ^ 1);
-        if (lane == 0) mbar_expect_tx(&full[stage], 2 * KT * NB * sizeof(double));
-        __syncwarp();
-        double* dst = stages + stage * STAGE_DOUBLES;
-        if (lane < KT) bulk_g2s(dst + lane * LDS_T, srcA + (int64_t)(c * KT + lane) * ldA, NB * sizeof(double), &full[stage]);
-        else bulk_g2s(dst + KT * LDS_T + (lane - KT) * LDS_T, srcB + (int64_t)(c * KT + lane - KT) * ldB, NB * sizeof(double), &full[stage]);
+        if (lane == 0) {
+          mbar_expect_tx(&full[stage], 2 * KT * NB * sizeof(double));
+          double* dst = stages + stage * STAGE_DOUBLES;
+          const double* sa = srcA + (int64_t)(c * KT) * ldA;
+          const double* sb = srcB + (int64_t)(c * KT) * ldB;
+#pragma unroll
+          for (int r = 0; r < KT; ++r) {
+            bulk_g2s(dst + r * LDS_T, sa + r * ldA, NB * sizeof(double), &full[stage]);
+            bulk_g2s(dst + (KT + r) * LDS_T, sb + r * ldB, NB * sizeof(double), &full[stage]);
+          }
+        }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         if (++issued == NSTAGE && tc.post) { for (; rissued < NRBUF; ++rissued) issue_r(rissued); }
       }
