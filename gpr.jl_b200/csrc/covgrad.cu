@@ -44,7 +44,7 @@ __device__ __forceinline__ void kfun(double r2, double sf2, double& kf, double& 
 }
 
 __device__ __forceinline__ void lower_tile(int bx, int& i, int& j) {
-  i = (int)((sqrt(8.0 * bx + 1.0) - 1.0) * 0.5);
+  i = (int)((__fsqrt_rn(8.0f * bx + 1.0f) - 1.0f) * 0.5f);  // approximate, corrected by the two loops below
   while ((i + 1) * (i + 2) / 2 <= bx) ++i;
   while (i * (i + 1) / 2 > bx) --i;
   j = bx - i * (i + 1) / 2;
@@ -487,16 +487,19 @@ __global__ void __launch_bounds__(GRAD_THREADS, LEAN ? 3 : 2) k_grad_tiles(GradA
         const double2 u = *reinterpret_cast<const double2*>(Xj + p * CW + 16 * cb + 2 * ty);
         xc[2 * cb] = u.x; xc[2 * cb + 1] = u.y;
       }
-      double s0 = 0.0, s1 = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four independent FMA chains (two left the DFMA latency exposed)
 #pragma unroll
       for (int a = 0; a < 8; a += 2)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 4; b += 2) {
           const double d0 = xr[a] - xc[b], d1 = xr[a + 1] - xc[b];
+          const double d2 = xr[a] - xc[b + 1], d3 = xr[a + 1] - xc[b + 1];
           s0 = fma(m[a][b], d0 * d0, s0);
           s1 = fma(m[a + 1][b], d1 * d1, s1);
+          s2 = fma(m[a][b + 1], d2 * d2, s2);
+          s3 = fma(m[a + 1][b + 1], d3 * d3, s3);
         }
-      red[(p0 + p) * NT + threadIdx.x] = s0 + s1;
+      red[(p0 + p) * NT + threadIdx.x] = (s0 + s1) + (s2 + s3);
     }
   }
   red[d * NT + threadIdx.x] = s_sig;
