@@ -218,6 +218,10 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   else if (!RAGGED && (g.mode == GEMM_CHOL_DIAG || (g.mode == GEMM_CHOL_TRAIL && tc.i == tc.j))) npred = nchunks;
   else if (!RAGGED && g.mode == GEMM_TRTRI_ROW) npred = NB / KT;
   const int diag_off = 4 * wn - 8 * wm;  // CHOL_DIAG: block (mi, ni) touches the lower triangle iff mi >= ni + diag_off
+  // LAUUM diagonal tiles are symmetric: beyond the leading (triangular-operand) k-block only the 8x8 blocks on or below
+  // the diagonal are accumulated, the store mirrors them into the upper half (the gradient stage reads whole tiles)
+  const bool lsym = !RAGGED && g.mode == GEMM_LAUUM && tc.i == tc.j;
+  const int sel_tri = diag_off >= 8 ? SEL_SKIP : diag_off == 4 ? SEL_TRI4 : diag_off == 0 ? SEL_TRI0 : SEL_FULL;
   const int sel_plain = ni_lim < 4 ? sel_cols(ni_lim) : sel_rows(mi_valid);  // (the compact layout is never ragged)
   {
     int stage = 0; uint32_t phase = 0;
@@ -237,8 +241,8 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
         else if (g.mode == GEMM_TRTRI_ROW) {                                          // columns <= 16c + 15 of the triangular B
           const int ni_lim = 2 * c + 2 - 4 * wn;
           sel = ni_lim <= 0 ? SEL_SKIP : ni_lim == 2 ? SEL_NI2 : SEL_FULL;
-        } else sel = diag_off >= 8 ? SEL_SKIP : diag_off == 4 ? SEL_TRI4 : diag_off == 0 ? SEL_TRI0 : SEL_FULL;
-      }
+        } else sel = sel_tri;
+      } else if (lsym) sel = sel_tri;
       chunk_dispatch(sel, acc, As + t * LDS_T + row0, As + (KT + t) * LDS_T + col0);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -267,9 +271,12 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         if (RAGGED && mi >= mi_valid) continue;
+        if (lsym && mi < ni + diag_off) continue;  // upper 8x8 blocks hold partial sums only: written by their mirror block
         const int r = wm * 64 + mi * 8 + gq, cc = wn * 32 + ni * 8 + 2 * t;
         out[r + (int64_t)cc * ldo] = sgn * acc[mi][ni][0];
         out[r + (int64_t)(cc + 1) * ldo] = sgn * acc[mi][ni][1];
+        if (lsym && mi > ni + diag_off)  // strictly-lower block: mirror (rows cc, cc + 1 of column r are adjacent)
+          *reinterpret_cast<double2*>(&out[cc + (int64_t)r * ldo]) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
       }
     GPRB_TL(6);
     return;

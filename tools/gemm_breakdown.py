@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 NB, KT = 128, 16
 
 
-def warp_dmma(mode, c, wm, wn, ragged, mi_valid, first_kb_chunks):
+def warp_dmma(mode, c, wm, wn, ragged, mi_valid, first_kb_chunks, sym=False):
     """8x8x4 DMMAs one consumer warp issues for main-loop chunk c (4 k4-steps x selected (mi, ni) blocks)."""
     mi_lim, ni_lim, off = mi_valid, 4, -64
     if not ragged:
@@ -22,6 +22,8 @@ def warp_dmma(mode, c, wm, wn, ragged, mi_valid, first_kb_chunks):
             off = 4 * wn - 8 * wm
         elif mode == "lauum" and c < first_kb_chunks:
             mi_lim = max(0, min(8, 2 * c + 2 - 8 * wm))
+        elif mode == "lauum" and sym:
+            off = 4 * wn - 8 * wm
         elif mode == "trtri_row" and c < NB // KT:
             ni_lim = max(0, min(4, 2 * c + 2 - 4 * wn))
     cnt = sum(1 for mi in range(mi_lim) for ni in range(ni_lim) if mi >= ni + off)
@@ -52,7 +54,7 @@ def launch_flops(mode, step, n):
             wm, wn = h, (3 - s4) if h else s4
             mi_valid = min(8, max(0, (rows_valid - wm * 64 + 7) // 8)) if ragged else 8
             for c in range(nchunks):
-                total += warp_dmma(mode, c, wm, wn, ragged, mi_valid, first_kb_chunks)
+                total += warp_dmma(mode, c, wm, wn, ragged, mi_valid, first_kb_chunks, sym=(i == j))
             if post:
                 kmax = (wn * 32 + 31) if post == 1 else min(wm * 64 + 63, rows_valid - 1)
                 for c in range(NB // KT):
