@@ -90,11 +90,12 @@ __device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int b
   return tc;
 }
 
-enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_MI4, SEL_MI6, SEL_NI1, SEL_NI2, SEL_NI3, SEL_TRI0, SEL_TRI4 };
+enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_MI4, SEL_MI6, SEL_NI1, SEL_NI2, SEL_NI3, SEL_TRI0, SEL_TRI4,
+       SEL_MLO2, SEL_MLO4, SEL_MLO6, SEL_MLO2_NI3, SEL_MLO4_NI3, SEL_MLO6_NI3, SEL_NLO2 };
 
 // One k-chunk (KT = 16) of a warp's 64x32 register tile restricted, at compile time, to the 8x8 blocks
-// (mi, ni) with mi < MI_LIM, ni < NI_LIM and mi >= ni + OFF: straight-line unpredicated DMMAs.
-template <int MI_LIM, int NI_LIM, int OFF>
+// (mi, ni) with MI_LO <= mi < MI_LIM, NI_LO <= ni < NI_LIM and mi >= ni + OFF: straight-line unpredicated DMMAs.
+template <int MI_LIM, int NI_LIM, int OFF, int MI_LO = 0, int NI_LO = 0>
 __device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* ap, const double* bp) {
   // ap / bp: this lane's fragment pointers at k4 = 0, i.e. base + t * LDS_T + row0 (resp. col0); both operands are
   // k-major in smem with row stride LDS_T
@@ -102,15 +103,15 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* 
   for (int k4 = 0; k4 < KT / 4; ++k4, ap += 4 * LDS_T, bp += 4 * LDS_T) {
     double a[8], b[4];
 #pragma unroll
-    for (int mi = 0; mi < MI_LIM; ++mi)
+    for (int mi = MI_LO; mi < MI_LIM; ++mi)
       if (mi >= OFF) a[mi] = ap[mi * 8];
 #pragma unroll
-    for (int ni = 0; ni < NI_LIM; ++ni)
+    for (int ni = NI_LO; ni < NI_LIM; ++ni)
       if (ni + OFF <= 7) b[ni] = bp[ni * 8];
 #pragma unroll
-    for (int mi = 0; mi < MI_LIM; ++mi)
+    for (int mi = MI_LO; mi < MI_LIM; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < NI_LIM; ++ni)
+      for (int ni = NI_LO; ni < NI_LIM; ++ni)
         if (mi >= ni + OFF) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
   }
 }
@@ -127,6 +128,13 @@ __device__ __forceinline__ void chunk_dispatch(int sel, double (&acc)[8][4][2], 
     case SEL_NI3: chunk_mma<8, 3, -64>(acc, ap, bp); break;
     case SEL_TRI0: chunk_mma<8, 4, 0>(acc, ap, bp); break;
     case SEL_TRI4: chunk_mma<8, 4, 4>(acc, ap, bp); break;
+    case SEL_MLO2: chunk_mma<8, 4, -64, 2>(acc, ap, bp); break;
+    case SEL_MLO4: chunk_mma<8, 4, -64, 4>(acc, ap, bp); break;
+    case SEL_MLO6: chunk_mma<8, 4, -64, 6>(acc, ap, bp); break;
+    case SEL_MLO2_NI3: chunk_mma<8, 3, -64, 2>(acc, ap, bp); break;
+    case SEL_MLO4_NI3: chunk_mma<8, 3, -64, 4>(acc, ap, bp); break;
+    case SEL_MLO6_NI3: chunk_mma<8, 3, -64, 6>(acc, ap, bp); break;
+    case SEL_NLO2: chunk_mma<8, 4, -64, 0, 2>(acc, ap, bp); break;
     default: chunk_mma<8, 4, -64>(acc, ap, bp); break;
   }
 }
@@ -320,8 +328,19 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     if (c * KT <= kmax) {
       const double* Rs = rbuf + buf * RBUF_DOUBLES + t * LDS_T;
       const double* Tc = Ts + (c * KT + t) * LDS_T;
-      if (tc.post == 1) chunk_dispatch(sel_plain, acc, Tc + row0, Rs + col0);
-      else chunk_dispatch(sel_plain, acc, Rs + row0, Tc + col0);
+      // triangular skip inside the warp tile: chunk c only meets output columns (post 1) / rows (post 2) x >= 16 c
+      int sel = sel_plain;
+      if (tc.post == 1) {
+        if (sel_plain == SEL_FULL && 2 * c - 4 * wn == 2) sel = SEL_NLO2;
+        chunk_dispatch(sel, acc, Tc + row0, Rs + col0);
+      } else {
+        const int lo = 2 * c - 8 * wm;  // first 8-row slab that meets chunk c: 0, 2, 4 or 6 here (c * KT <= kmax)
+        if (lo > 0) {
+          if (sel_plain == SEL_FULL) sel = lo == 2 ? SEL_MLO2 : lo == 4 ? SEL_MLO4 : SEL_MLO6;
+          else if (sel_plain == SEL_NI3) sel = lo == 2 ? SEL_MLO2_NI3 : lo == 4 ? SEL_MLO4_NI3 : SEL_MLO6_NI3;
+        }
+        chunk_dispatch(sel, acc, Rs + row0, Tc + col0);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rempty[buf]);

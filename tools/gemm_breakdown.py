@@ -59,7 +59,13 @@ def launch_flops(mode, step, n):
                 kmax = (wn * 32 + 31) if post == 1 else min(wm * 64 + 63, rows_valid - 1)
                 for c in range(NB // KT):
                     if c * KT <= kmax:
-                        total += 4 * mi_valid * 4
+                        mi_n, ni_n = mi_valid, 4
+                        if not ragged:  # triangular skip inside the warp tile (SEL_NLO2 / SEL_MLOx)
+                            if post == 1 and 2 * c - 4 * wn == 2:
+                                ni_n = 2
+                            if post == 2 and 2 * c - 8 * wm > 0:
+                                mi_n = 8 - (2 * c - 8 * wm)
+                        total += 4 * mi_n * ni_n
     return total * 512  # 8x8x4 MACs x 2
 
 
