@@ -70,7 +70,8 @@ def test_eval_parity_well_conditioned(gprb, system, n):
     assert g2 is None and np.array_equal(mll, mll2)
 
 
-@pytest.mark.parametrize("n,d", [(1, 1), (2, 13), (4, 26), (8, 3), (16, 2), (50, 5), (129, 4), (40, 62)])
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 13), (4, 26), (8, 3), (16, 2), (50, 5), (129, 4), (40, 62),
+                                 (150, 30), (150, 31), (200, 32), (140, 33)])  # gradient layouts: lean <= 30 < two-block <= 32 < multi-pass
 def test_tiny_n_and_minimal_coordinate_d(gprb, n, d):
     """The reference sweeps n = 2, 4, 8 ... (examples/noise.jl:64, hyperparameter.jl:50) and its minimal-coordinate
     experiments use d = 2..6 (examples/minimal_coordinates/*); both go through the same boundary."""
