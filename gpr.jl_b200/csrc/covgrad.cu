@@ -167,7 +167,10 @@ constexpr double GRAM_SMAX = 16.0;    // (d/4 + 2) eps * 16 < 4e-14 for d <= 62
 constexpr double GRAM_R2CUT = 1500.0; // exp(-750) underflows to zero: pairs beyond it are exact zeros either way
 
 template <int KIND>
-__global__ void __launch_bounds__(GA_THREADS, 2) k_assemble_gram(AssembleArgs g) {
+#ifndef GPRB_ASM_CTAS
+#define GPRB_ASM_CTAS 2
+#endif
+__global__ void __launch_bounds__(GA_THREADS, GPRB_ASM_CTAS) k_assemble_gram(AssembleArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = g.d, dpad = (d + 3) & ~3;
   double* Zi = reinterpret_cast<double*>(smem_raw);   // [dpad][LDS_T]  row-input tile, one padded row per dimension
