@@ -166,11 +166,11 @@ constexpr int GA_LDJ = GA_CW + 4;     // padded row of the column-input tile (co
 constexpr double GRAM_SMAX = 16.0;    // (d/4 + 2) eps * 16 < 4e-14 for d <= 62
 constexpr double GRAM_R2CUT = 1500.0; // exp(-750) underflows to zero: pairs beyond it are exact zeros either way
 
-template <int KIND>
-#ifndef GPRB_ASM_CTAS
-#define GPRB_ASM_CTAS 2
-#endif
-__global__ void __launch_bounds__(GA_THREADS, GPRB_ASM_CTAS) k_assemble_gram(AssembleArgs g) {
+// CTAS = resident CTAs per SM the kernel is compiled for: 3 (80 registers, a few spilled words in the prologue) whenever
+// three 71 KB input/cross-term regions fit (d <= 28: 5.7 -> 5.15 ms per 400 GPs, the phases of three CTAs interleave
+// better than those of two), else 2.
+template <int KIND, int CTAS>
+__global__ void __launch_bounds__(GA_THREADS, CTAS) k_assemble_gram(AssembleArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = g.d, dpad = (d + 3) & ~3;
   double* Zi = reinterpret_cast<double*>(smem_raw);   // [dpad][LDS_T]  row-input tile, one padded row per dimension
@@ -585,9 +585,15 @@ int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream) {
     const size_t zreg = std::max((size_t)dpad * (LDS_T + GA_LDJ), (size_t)GA_CW * LDS_T);  // input tiles, later the cross-term tile
     const size_t smem = (zreg + 3 * (MAX_D + 2) + NB + GA_CW) * sizeof(double) + 16;
     dim3 grid(a.J * (a.J + 1) / 2 * (NB / GA_CW), count);
-#define GPRB_GA_CASE(K)                                 \
-  rc = set_smem(k_assemble_gram<K>, smem);              \
-  if (!rc) k_assemble_gram<K><<<grid, GA_THREADS, smem, stream>>>(a);
+    const bool three = 3 * (smem + 1024) <= 227 * 1024;  // three CTAs per SM fit (1 KB per CTA is reserved by the driver)
+#define GPRB_GA_CASE(K)                                                                  \
+  if (three) {                                                                           \
+    rc = set_smem(k_assemble_gram<K, 3>, smem);                                          \
+    if (!rc) k_assemble_gram<K, 3><<<grid, GA_THREADS, smem, stream>>>(a);               \
+  } else {                                                                               \
+    rc = set_smem(k_assemble_gram<K, 2>, smem);                                          \
+    if (!rc) k_assemble_gram<K, 2><<<grid, GA_THREADS, smem, stream>>>(a);               \
+  }
     switch (a.kind) {
       case GPRB_KERNEL_SE_ARD: GPRB_GA_CASE(0) break;
       case GPRB_KERNEL_MAT12_ARD: GPRB_GA_CASE(1) break;
