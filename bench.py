@@ -253,11 +253,19 @@ def main():
         X_pin[t] = tr["X"].T
     Xs = [X_pin[t].T for t in range(T)]  # d x n column-major views
     ymm = torch.from_numpy(batch.ymm.copy()).pin_memory().numpy()
+    host_ms = [0.0, 0.0]  # upload (gprb_datasets_update + gprb_batch_set_targets) / evaluation (gprb_eval), host clock
+
     def step_host(i):
+        t_a = time.perf_counter()
         batch.update_data(Xs, ymm)
-        return batch.eval(theta=thetas[i], grad=True)
+        t_b = time.perf_counter()
+        out = batch.eval(theta=thetas[i], grad=True)
+        host_ms[0] += (t_b - t_a) * 1e3
+        host_ms[1] += (time.perf_counter() - t_b) * 1e3
+        return out
     step_host(0)
     barrier()
+    host_ms[0] = host_ms[1] = 0.0
     t0 = time.perf_counter()
     for k in range(args.steps):
         mll_h, grad_h, info_h = step_host(args.warmup + k)
@@ -337,7 +345,8 @@ def main():
                        "theta": ("config.json CP_MAX2048" if args.system == "CP" else "theta_0 of the config (data.CONFIGS)") + " + 0.1*N(0,I), fresh per step",
                        "l2": f"working set {2 * B * batch.n * batch.n * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "info_ok": info_ok, "parallelism": f"trial-sharded x{world}, per-step NCCL all-gather of results"},
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "upload_ms_per_step": host_ms[0] / args.steps, "eval_ms_per_step": host_ms[1] / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
             "value_only": {"value": value_only, "unit": "evals/s", "frac_fp64_peak": (n ** 3 / 3 + 1.5 * d * n ** 2 + 2 * n ** 2) * value_only / world / 1e12 / peak,
                            "note": "logML without gradient (line-search trials of optimize!): assembly + Cholesky + solve"}}

@@ -49,7 +49,9 @@ struct gprb_ctx {
   int clock_khz = 0;
   int64_t l2_bytes = 0;
   int64_t launches = 0;
-  cudaStream_t upload = nullptr;  // dataset uploads + input transposes (non-blocking stream)
+  cudaStream_t upload = nullptr;   // dataset uploads (non-blocking stream)
+  cudaStream_t upload2 = nullptr;  // input transposes of a batched upload, behind upload_ev
+  cudaEvent_t upload_ev = nullptr;
 };
 
 struct gprb_dataset {

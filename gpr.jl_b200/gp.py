@@ -234,11 +234,28 @@ class GPE:
         self.kernel = kernel
         self.logNoise = float(logNoise)
         self.dim, self.nobs = X.shape
-        self.mll = float("nan")
-        self.dmll = None
-        self.info = 0
         self._batch = None
         self._slot = -1
+        self._res = (float("nan"), None, 0)  # (mll, dmll, info) while the GP is not resident in a batch
+
+    # Results of the last evaluation.  While the GP is resident in a GPBatch they are views into the batch's result
+    # arrays (one vectorised store per evaluation instead of a Python loop over the GPs of the batch).
+    @property
+    def mll(self):
+        b = self._batch
+        return float(b._mll[self._slot]) if b is not None else self._res[0]
+
+    @property
+    def dmll(self):
+        b = self._batch
+        if b is None:
+            return self._res[1]
+        return b._grad[self._slot].copy() if b._has_grad[self._slot] else None
+
+    @property
+    def info(self):
+        b = self._batch
+        return int(b._info[self._slot]) if b is not None else self._res[2]
 
     # GaussianProcesses.get_params order: [logNoise; mean params (none); kernel params]
     def get_params(self):
@@ -286,6 +303,15 @@ class GPBatch:
         self._keep = []
         ds_handles = (C.c_void_p * self.B)()
         ymm = np.empty((self.B, n))
+        # per-GP results of the last evaluation (GPE.mll / .dmll / .info read them); seeded with what the GPs carry
+        prev = [(g.mll, g.dmll, g.info) for g in gps]
+        self._mll = np.array([r[0] for r in prev], dtype=np.float64)
+        self._info = np.array([r[2] for r in prev], dtype=np.int32)
+        self._grad = np.full((self.B, self.P), np.nan)
+        self._has_grad = np.zeros(self.B, dtype=bool)
+        for b, r in enumerate(prev):
+            if r[1] is not None:
+                self._grad[b], self._has_grad[b] = r[1], True
         for b, g in enumerate(gps):
             key = id(g.x)
             if key not in self._ds:
@@ -317,6 +343,7 @@ class GPBatch:
         self._ds = {}
         for g in getattr(self, "gps", []):
             if g._batch is self:
+                g._res = (g.mll, g.dmll, g.info)  # the GP keeps its last results
                 g._batch, g._slot = None, -1
 
     def __del__(self):
@@ -367,10 +394,10 @@ class GPBatch:
         self.lib.check(self.lib.dll.gprb_eval(
             self.handle, _d(theta), act.ctypes.data_as(C.POINTER(C.c_uint8)) if act is not None else None,
             _d(mll), _d(g), info.ctypes.data_as(C.POINTER(C.c_int32))))
-        for b, gp in enumerate(self.gps):
-            if act is None or act[b]:
-                gp.mll, gp.info = float(mll[b]), int(info[b])
-                gp.dmll = g[b].copy() if grad else None
+        sel = slice(None) if act is None else act.astype(bool)
+        self._mll[sel], self._info[sel], self._has_grad[sel] = mll[sel], info[sel], bool(grad)
+        if grad:
+            self._grad[sel] = g[sel]
         return mll, g, info
 
     def eval_mixed(self, theta, mode):
@@ -383,10 +410,9 @@ class GPBatch:
         info = np.zeros(self.B, dtype=np.int32)
         self.lib.check(self.lib.dll.gprb_eval_mixed(self.handle, _d(theta), mode.ctypes.data_as(C.POINTER(C.c_uint8)),
                                                     _d(mll), _d(g), info.ctypes.data_as(C.POINTER(C.c_int32))))
-        for b, gp in enumerate(self.gps):
-            if mode[b]:
-                gp.mll, gp.info = float(mll[b]), int(info[b])
-                gp.dmll = g[b].copy() if mode[b] == 2 else None
+        sel, wg = mode != 0, mode == 2
+        self._mll[sel], self._info[sel], self._has_grad[sel] = mll[sel], info[sel], wg[sel]
+        self._grad[wg] = g[wg]
         return mll, g, info
 
     def eval_device(self, theta_ptr, mll_ptr, grad_ptr=None, info_ptr=None, stream=0):
@@ -440,7 +466,7 @@ class GPBatch:
         out = []
         for b, gp in enumerate(self.gps):
             r = res[b]
-            gp.mll, gp.info, gp.dmll = r.mll, r.info, None
+            self._mll[b], self._info[b], self._has_grad[b] = r.mll, r.info, False
             out.append({"minimizer": theta[b].copy(), "minimum": -r.mll, "g_norm": r.g_norm, "iterations": r.iterations,
                         "f_calls": r.f_calls, "g_calls": r.fg_calls, "converged": bool(r.converged),
                         "ls_failed": bool(r.ls_failed), "info": r.info})
