@@ -97,7 +97,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool r
         for (int q = 1; q <= 6; ++q) { unsigned long long cur = t[q] ? t[q] : prev; ph[q - 1] += (double)(cur - prev); prev = cur; }
         tot += (double)(t[6] - t[0]); waitc += (double)t[7]; ++cnt;
       }
-      if (cnt) fprintf(stderr, "TL mode %d step %2d tiles %6zu  fill %6.2f main %7.2f cin %6.2f park %6.2f post %6.2f store %6.2f  total %7.2f us  (operand wait in main %6.2f us)\n",
+      if (cnt) fprintf(stderr, "TL mode %d step %2d tiles %6zu  fill %6.2f main %7.2f cin %6.2f park %6.2f post %6.2f store %6.2f  total %7.2f us  (operand wait in main, after the first chunk %6.2f us)\n",
                        a.mode, a.step, cnt, ph[0] / cnt / 1e3, ph[1] / cnt / 1e3, ph[2] / cnt / 1e3, ph[3] / cnt / 1e3, ph[4] / cnt / 1e3, ph[5] / cnt / 1e3, tot / cnt / 1e3, waitc / cnt / 1965.0);
     }
     return r;

@@ -237,7 +237,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
 #ifdef GPRB_TIMELINE
       const long long w0 = clock64();
       mbar_wait(&full[stage], phase);
-      tl_wait += clock64() - w0;
+      if (c > 0) tl_wait += clock64() - w0;  // the wait for the first chunk is the `fill` phase
 #else
       mbar_wait(&full[stage], phase);
 #endif
