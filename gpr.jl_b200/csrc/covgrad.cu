@@ -312,13 +312,12 @@ static_assert(GRAD_CW == 32, "thread mapping below assumes 32-column blocks");
 constexpr int GRAD_DH = 32;  // input dimensions resident at a time: d > 32 (FB: d = 52) streams its input tiles in two passes
                              // so that the CTA stays at ~105 KB of smem and two CTAs fit an SM for every d
 
-// LEAN (d <= 30, where the (d + 2) x 128 reduction buffer fits the K^-1 landing zone alone): the K block is not landed in
+// LEAN (every d but 31 and 32: the rows of one pass, <= 32, fit the K^-1 landing zone that the reduction reuses): the K block is not landed in
 // shared memory but prefetched into 32 registers per thread before the wait on the bulk copies - 66 KB per CTA, so THREE
 // CTAs share an SM and the FP64 phase of one always has the copies / reductions of two others to hide behind (with two
 // CTAs per SM the DFMA pipe sat at 56 %: a CTA spends longer outside its FP64 phase than inside).
 template <int KIND, bool MULTI, bool LEAN>  // MULTI = false: d <= GRAD_DH, one resident pass (the common case compiles without the pass logic)
 __global__ void __launch_bounds__(GRAD_THREADS, LEAN ? 3 : 2) k_grad_tiles(GradArgs g) {
-  static_assert(!(MULTI && LEAN), "the lean layout is single-pass");
   constexpr int CW = GRAD_CW, NT = GRAD_THREADS, NQ = NB / CW, DH = MULTI ? GRAD_DH : MAX_D + 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = g.d, dh = min(d, DH), npass = MULTI ? (d + DH - 1) / DH : 1;
@@ -328,7 +327,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, LEAN ? 3 : 2) k_grad_tiles(GradA
   double* Xj = Xi + dh * NB;                          // [dh][CW]
   double* w = Xj + dh * CW;                           // [MAX_D]
   uint64_t* bar = reinterpret_cast<uint64_t*>(w + MAX_D);
-  double* red = Ki;                                   // [(d + 2)][NT] <= 2 * CW * NB doubles for d <= 62
+  double* red = Ki;                                   // [rows of one pass (+ 2)][NT]: <= 32 rows in the lean layout, <= 34 otherwise
   const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
   if (g.fail[gp] != 0) return;  // failed factorisation: k_grad_reduce reports NaN, nothing to sum
   const int tile = blockIdx.x / NQ, cq = blockIdx.x - tile * NQ;
@@ -472,6 +471,9 @@ __global__ void __launch_bounds__(GRAD_THREADS, LEAN ? 3 : 2) k_grad_tiles(GradA
     }
   }
   __syncthreads();  // every thread is done with the landed blocks: the space becomes `red`
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double wt = (ti == tj) ? 1.0 : 2.0;
+  double* part = g.part + ((int64_t)gp * gridDim.x + blockIdx.x) * (d + 2);
   // phase 2 (FP64 pipe): per-dimension weighted sums; one scalar per (p, thread) parked in smem.  Passes start with
   // the resident one (the last pass after a Matern distance sweep, pass 0 otherwise).
   for (int qq = 0; qq < npass; ++qq) {
@@ -502,27 +504,30 @@ __global__ void __launch_bounds__(GRAD_THREADS, LEAN ? 3 : 2) k_grad_tiles(GradA
           s2 = fma(m[a][b + 1], d2 * d2, s2);
           s3 = fma(m[a + 1][b + 1], d3 * d3, s3);
         }
-      red[(p0 + p) * NT + threadIdx.x] = (s0 + s1) + (s2 + s3);
+      red[p * NT + threadIdx.x] = (s0 + s1) + (s2 + s3);
     }
-  }
-  red[d * NT + threadIdx.x] = s_sig;
-  red[(d + 1) * NT + threadIdx.x] = s_tr;
-  __syncthreads();
-  // fixed-order block reduction: warp v sums rows v, v + 4, ...
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double wt = (ti == tj) ? 1.0 : 2.0;
-  double* part = g.part + ((int64_t)gp * gridDim.x + blockIdx.x) * (d + 2);
-  for (int row = warp; row < d + 2; row += NT / 32) {
-    double s = 0.0;
+    // Every pass is reduced on its own (its rows never exceed the 32 the lean landing zone holds); the two scalar sums
+    // ride with the last - shortest - pass.  The __syncthreads at the top of need_pass orders the next pass's writes.
+    int nrows = pc;
+    if (q == npass - 1) {
+      red[pc * NT + threadIdx.x] = s_sig;
+      red[(pc + 1) * NT + threadIdx.x] = s_tr;
+      nrows += 2;
+    }
+    __syncthreads();
+    // fixed-order block reduction: warp v sums rows v, v + 4, ...
+    for (int row = warp; row < nrows; row += NT / 32) {
+      double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < NT / 32; ++k) s += red[row * NT + lane + 32 * k];
+      for (int k = 0; k < NT / 32; ++k) s += red[row * NT + lane + 32 * k];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) {
-      // part layout: [0] trace(Q) part, [1..d] sum Q g Delta_p^2, [d+1] sum Q K_f
-      if (row < d) part[1 + row] = wt * s;
-      else if (row == d) part[d + 1] = wt * s;
-      else part[0] = s;  // trace lives on diagonal tiles only (weight 1)
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) {
+        // part layout: [0] trace(Q) part, [1..d] sum Q g Delta_p^2, [d+1] sum Q K_f
+        if (row < pc) part[1 + p0 + row] = wt * s;
+        else if (row == pc) part[d + 1] = wt * s;
+        else part[0] = s;  // trace lives on diagonal tiles only (weight 1)
+      }
     }
   }
 }
@@ -622,7 +627,7 @@ int launch_grad(const GradArgs& a, int count, cudaStream_t stream) {
   // lean layout (three CTAs per SM) whenever the (d + 2) x 128 reduction buffer fits the K^-1 landing zone;
   // GPRB200_GRAD_LEAN=0 forces the two-block layout (A/B comparisons)
   static const bool allow_lean = [] { const char* e = getenv("GPRB200_GRAD_LEAN"); return !(e && e[0] == '0'); }();
-  const bool lean = allow_lean && (a.d + 2) * GRAD_THREADS <= GRAD_CW * NB;
+  const bool lean = allow_lean && (a.d + 2 <= GRAD_CW || a.d > GRAD_DH);  // single pass of <= 30 dims, or passes of 32 + a short last one
   const size_t smem = pw_smem(a.d, true, lean);
   dim3 grid(a.J * (a.J + 1) / 2 * (NB / GRAD_CW), count);
   int rc = 0;
@@ -630,8 +635,10 @@ int launch_grad(const GradArgs& a, int count, cudaStream_t stream) {
   rc = set_smem(k_grad_tiles<K, M, L>, smem);                             \
   if (!rc) k_grad_tiles<K, M, L><<<grid, GRAD_THREADS, smem, stream>>>(a);
 #define GPRB_GRAD_CASE(K)                                                 \
-  if (lean) { GPRB_GRAD_LAUNCH(K, false, true) }                          \
-  else if (a.d <= GRAD_DH) { GPRB_GRAD_LAUNCH(K, false, false) }          \
+  if (a.d <= GRAD_DH) {                                                   \
+    if (lean) { GPRB_GRAD_LAUNCH(K, false, true) }                        \
+    else { GPRB_GRAD_LAUNCH(K, false, false) }                            \
+  } else if (lean) { GPRB_GRAD_LAUNCH(K, true, true) }                    \
   else { GPRB_GRAD_LAUNCH(K, true, false) }
   switch (a.kind) {
     case GPRB_KERNEL_SE_ARD: GPRB_GRAD_CASE(0) break;
