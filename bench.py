@@ -119,6 +119,18 @@ class CpuArm:
         self.pool.join()
 
 
+def julia_probe():
+    """re-probe the reference's toolchain on the box the benchmark runs on (its own CPU path needs Julia)."""
+    import shutil
+    exe = shutil.which("julia")
+    if not exe:
+        return "absent"
+    try:
+        return subprocess.run([exe, "--version"], capture_output=True, text=True, timeout=20).stdout.strip() or "present"
+    except Exception:
+        return "present (version probe failed)"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,7 +153,7 @@ def run_reference(args):
                        "sample": f"one step = {arm.cores} concurrent logML+gradient evaluations (one n=2000 GP per host core)"},
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": arm.cores, "kind": "port",
                              "sample": f"{evals} evaluations of n=2000,d=26 GPs, {arm.cores} worker processes x 1 BLAS thread (oracle: restated "
-                                       "GaussianProcesses.jl path on scipy OpenBLAS; Julia absent, trials in parallel like core.jl:28)"},
+                                       f"GaussianProcesses.jl path on scipy OpenBLAS; julia on this box: {julia_probe()}; trials in parallel like core.jl:28)"},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
