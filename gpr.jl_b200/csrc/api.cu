@@ -726,6 +726,9 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
                     (int)b->npad, J, 0, GEMM_FWD_ROW, nv};
         ga.Tm = b->pT; ga.t_stride = b->npad * PT; ga.ldt = PT;
         ga.ncols = ta.mc;
+        // few GPs (large n, or the reference's single-GP call pattern): narrower tiles, so that a launch still fills the SMs
+        ga.colw = B >= b->ctx->sm_count ? PT : (2 * B >= b->ctx->sm_count ? PT / 2 : PT / 4);
+        const int ntl = (ta.mc + ga.colw - 1) / ga.colw;
         // the GPs are dealt over the stream groups: the dependent chain of J launches of one group fills the wave
         // tails of the others (B tiles per launch are not a multiple of the SM count)
         const int S = (B >= 8 * b->nstreams) ? b->nstreams : 1;
@@ -737,7 +740,7 @@ int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_st
           ga.gp_off = g0;
           for (int i = 0; i < J; ++i) {
             ga.step = i;
-            if ((rc = launch_tile_gemm(ga, 1, g1 - g0, ss))) return rc;
+            if ((rc = launch_tile_gemm(ga, ntl, g1 - g0, ss))) return rc;
             b->ctx->launches++;
           }
           if (s > 0) {

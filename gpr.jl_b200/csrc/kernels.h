@@ -25,6 +25,7 @@ struct GemmArgs {
   int64_t t_stride = 0;
   int ldt = 0;
   int ncols = 128;      // valid test columns of the block (< 128: compact warp layout skips the padding columns)
+  int colw = 128;       // columns per FWD_ROW tile (128, 64 or 32): tile bx owns columns bx*colw .. of the block
   int gp_off = 0;       // first GP of this launch when `list` is null (stream groups of gprb_predict)
   const int32_t* fail = nullptr;     // [B] per-GP failure flag: tiles of a GP whose factorisation already broke down exit at once
   unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)

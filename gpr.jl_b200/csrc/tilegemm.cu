@@ -167,9 +167,14 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   // step) use a compact layout: the nblk = ceil(ncols / 8) valid 8-column blocks are dealt over the four column groups
   // (extras to groups 0, 1, 3 so the SMSP pairs {0,3} / {1,2} stay balanced) and every warp runs the chunk body
   // specialised to its own block count - the padding columns are neither multiplied nor loaded nor stored.
+  // A block may also be split into narrower tiles (g.colw = 64 or 32 columns, one CTA each) when a launch would otherwise
+  // have too few tiles to fill the SMs (few, large GPs; the single-GP call pattern): the compact layout then spreads the
+  // tile's few column blocks over all eight warps.  Ragged tiles run it with the full-row chunk bodies (the padding rows of
+  // the A operand only reach accumulator rows that are never stored or parked).
   int cbase = wn * 32, ni_lim = 4;
-  if (fwd && !RAGGED && g.ncols < NB) {
-    const int nblk = (g.ncols + 7) >> 3, q = nblk >> 2, rem = nblk & 3;
+  const int ncols_tile = fwd ? min(g.colw, g.ncols - tc.j * g.colw) : NB;
+  if (fwd && ncols_tile < NB) {
+    const int nblk = (ncols_tile + 7) >> 3, q = nblk >> 2, rem = nblk & 3;
     const int w0 = q + (rem >= 1), w1 = q + (rem >= 2), w2 = q, w3 = q + (rem >= 3);
     ni_lim = wn == 0 ? w0 : wn == 1 ? w1 : wn == 2 ? w2 : w3;
     cbase = 8 * (wn == 0 ? 0 : wn == 1 ? w0 : wn == 2 ? w0 + w1 : w0 + w1 + w2);
@@ -181,7 +186,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   // into the accumulator registers while the first operand chunks are still in flight: the 64 global loads per
   // thread need no extra registers and their latency hides behind the pipeline fill.  After the k-loop
   // acc = sum - Cin = -(Cin - sum); the sign is folded into the stores below.
-  const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * NB;
+  const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * (fwd ? g.colw : NB);
   double acc[8][4][2];
   if (fwd) {
     const double* Tin = g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt;
@@ -230,7 +235,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   // the diagonal are accumulated, the store mirrors them into the upper half (the gradient stage reads whole tiles)
   const bool lsym = !RAGGED && g.mode == GEMM_LAUUM && tc.i == tc.j;
   const int sel_tri = diag_off >= 8 ? SEL_SKIP : diag_off == 4 ? SEL_TRI4 : diag_off == 0 ? SEL_TRI0 : SEL_FULL;
-  const int sel_plain = ni_lim < 4 ? sel_cols(ni_lim) : sel_rows(mi_valid);  // (the compact layout is never ragged)
+  const int sel_plain = ni_lim < 4 ? sel_cols(ni_lim) : sel_rows(mi_valid);  // column-limited bodies run all 8 row slabs
   {
     int stage = 0; uint32_t phase = 0;
     for (int c = 0; c < nchunks; ++c) {
@@ -429,25 +434,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
       }
     };
     int issued = 0;  // main chunks issued so far; the post-multiplier prefetch follows the first ring fill
+    // bytes of one B-operand row: a narrow FWD_ROW tile only owns colw columns of the right-hand-side row
+    const uint32_t bbytes = (uint32_t)((g.mode == GEMM_FWD_ROW ? g.colw : NB) * sizeof(double));
     for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
       const double* srcA; const double* srcB; int64_t ldA, ldB;
       if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }
       else { srcA = Lm + (int64_t)tc.i * NB + (int64_t)kb * NB * npad; ldA = npad; }
       if (kb == tc.b_diag_kb) { srcB = DinvT + (int64_t)kb * NB * NB; ldB = NB; }
-      else if (g.mode == GEMM_FWD_ROW) { srcB = g.Tm + (int64_t)gp * g.t_stride + (int64_t)tc.j * NB + (int64_t)kb * NB * g.ldt; ldB = g.ldt; }
+      else if (g.mode == GEMM_FWD_ROW) { srcB = g.Tm + (int64_t)gp * g.t_stride + (int64_t)tc.j * g.colw + (int64_t)kb * NB * g.ldt; ldB = g.ldt; }
       else { srcB = Lm + (int64_t)tc.j * NB + (int64_t)kb * NB * npad; ldB = npad; }
       const int cend = (kb == g.J - 1) ? last_kb_chunks : NB / KT;
       for (int c = 0; c < cend; ++c) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
-          mbar_expect_tx(&full[stage], 2 * KT * NB * sizeof(double));
+          mbar_expect_tx(&full[stage], KT * (NB * sizeof(double) + bbytes));
           double* dst = stages + stage * STAGE_DOUBLES;
           const double* sa = srcA + (int64_t)(c * KT) * ldA;
           const double* sb = srcB + (int64_t)(c * KT) * ldB;
 #pragma unroll
           for (int r = 0; r < KT; ++r) {
             bulk_g2s(dst + r * LDS_T, sa + r * ldA, NB * sizeof(double), &full[stage]);
-            bulk_g2s(dst + (KT + r) * LDS_T, sb + r * ldB, NB * sizeof(double), &full[stage]);
+            bulk_g2s(dst + (KT + r) * LDS_T, sb + r * ldB, bbytes, &full[stage]);
           }
         }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }

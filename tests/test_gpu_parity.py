@@ -204,18 +204,22 @@ def test_predict_tiled_and_gemv_paths(gprb, system, n, m, kind):
     np.testing.assert_allclose(mu3, mu, rtol=1e-12, atol=1e-14)
 
 
-def test_predict_compact_columns_and_stream_groups(gprb):
+@pytest.mark.parametrize("ntrials,ms", [(8, (1, 8, 9, 23, 33, 47, 56, 60, 77, 88, 100, 104, 105, 113, 121, 128)),
+                                        (20, (5, 40, 64, 65, 100, 128)), (38, (7, 100, 128))])
+def test_predict_compact_columns_and_stream_groups(gprb, ntrials, ms):
     """Every width of the compact FWD_ROW column layout (1 .. 16 valid 8-column blocks, incl. the reference's m = 100
-    test states) on a batch large enough (32 GPs) for the per-stream GP groups of gprb_predict; n = 300 mixes full
-    block rows (compact layout) with the ragged last block row (default layout)."""
+    test states) on batches large enough for the per-stream GP groups of gprb_predict, at the three tile widths the
+    batch size selects (B = 32: 32-column tiles, B = 80: 64, B = 152: 128); n = 300 mixes full block rows with the
+    ragged last block row."""
     from gpr_jl_b200 import data
-    trials = [data.make_trial("CP", 300, seed=900 + t, n_test=128) for t in range(8)]
+    trials = [data.make_trial("CP", 300, seed=900 + t, n_test=128) for t in range(ntrials)]
     th = data.theta0("CP", trials[0]["X"])
     th[1:-1] -= 1.0
     rng = np.random.default_rng(5)
     thetas = [np.tile(th, (4, 1)) + 0.03 * rng.standard_normal((4, th.size)) for _ in trials]
     batch = build_batch(gprb, trials, thetas)
-    assert batch.B == 32
+    B = batch.B
+    assert B == 4 * ntrials
     batch.eval(grad=False)
     ref = oracle_all(trials, thetas, grad=False)
     Xs = trials[0]["Xtest"]
@@ -223,11 +227,12 @@ def test_predict_compact_columns_and_stream_groups(gprb):
     for b, r in enumerate(ref):
         X = np.ascontiguousarray(trials[b // 4]["X"].T)
         want.append(go.predict(X, thetas[b // 4][b % 4], r["state"], np.ascontiguousarray(Xs.T)))
-    for m in (1, 8, 9, 23, 33, 47, 56, 60, 77, 88, 100, 104, 105, 113, 121, 128):
+    for m in ms:
         mu, var = batch.predict_y(Xs[:, :m])
-        for b in range(32):
+        for b in range(B):
             assert rel(mu[b], want[b][0][:m]) <= 1e-9, (m, b)
             np.testing.assert_allclose(var[b], want[b][1][:m], rtol=1e-9, atol=1e-13, err_msg=f"m={m} b={b}")
+    batch.close()
 
 
 def test_mean_function_plugin(gprb):
