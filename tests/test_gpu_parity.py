@@ -502,6 +502,13 @@ def test_full_size_properties_n2000(gprb):
     r = go.eval_mll(X, tr["Y"][1], th, with_grad=True)
     assert abs(mll[1] - r["mll"]) <= 1e-8 * abs(r["mll"])
     assert rel(grad[1], r["grad"]) <= 1e-8
+    # the reference's prediction shape at full size: 100 test states per GP (predictdynamics.jl:11-19)
+    r1 = go.eval_mll(X, tr["Y"][1], th, with_grad=False, return_state=True)
+    Xs = data.make_trial("CP", 8, seed=77, n_test=100)["Xtest"]
+    mu, var = batch.predict_y(Xs)
+    m_o, v_o = go.predict(X, th, r1["state"], np.ascontiguousarray(Xs.T))
+    assert rel(mu[1], m_o) <= 1e-9
+    np.testing.assert_allclose(var[1], v_o, rtol=1e-9, atol=1e-13)
     v = np.random.default_rng(0).standard_normal(th.size)
     v /= np.linalg.norm(v)
     h = 1e-5
