@@ -55,12 +55,17 @@ static void free_batch(gprb_batch* b) {
   delete b;
 }
 
-// Enqueue one evaluation of the GPs in list[off .. off+count) on `st`: assembly, Cholesky and solve for all of them,
-// inverse + fused gradient for the first `ngrad` entries of the segment (the host orders value+gradient GPs first).
-static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool right_looking, cudaStream_t st, bool prof) {
+// Enqueue one evaluation of the GPs in list[off .. off+count) on `st`: inverse + fused gradient for the first `ngrad`
+// entries of the segment (the host orders value+gradient GPs first); assembly, Cholesky and solve for all entries but
+// the first `nreuse` (<= ngrad), whose factor, alpha and mll of the previous evaluation at the same theta are still
+// resident (the optimiser asks for the gradient at the point its line search just accepted).
+static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nreuse, bool right_looking, cudaStream_t st,
+                            bool prof) {
   if (count <= 0) return 0;
   const bool with_grad = ngrad > 0;
-  const int32_t* list = b->list + off;
+  const int32_t* glist = b->list + off;     // inverse + gradient: glist[0 .. ngrad)
+  const int32_t* list = glist + nreuse;     // assembly, factorisation, solves: list[0 .. count)
+  count -= nreuse;
   const int J = b->J;
   const int64_t ms = b->npad * b->npad, dstride = (int64_t)J * NB * NB;
   int rc;
@@ -109,6 +114,10 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool r
 #endif
   };
   if (prof) { b->gemm_ev_used = 0; cudaEventRecord(b->ev[0], st); }
+  const int nv = (int)((b->n + KT - 1) / KT * KT);
+  GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, b->KinvD, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG, nv};
+  ga.fail = b->fail;
+  if (count > 0) {
   // Small passes are latency bound (one dependent chain of 3 J launches): they use the right-looking factorisation,
   // whose launches are short and wide, instead of the left-looking one, whose k-loops grow with the column index.
   AssembleArgs aa{b->Xtptr, b->theta, b->jitter, b->A, nullptr, b->fail, list, ms, (int)b->n, (int)b->npad, b->d, J, b->kind};
@@ -116,9 +125,6 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool r
   if ((rc = launch_assemble(aa, count, st))) return rc;
   ++launches;
   if (prof) cudaEventRecord(b->ev[1], st);
-  const int nv = (int)((b->n + KT - 1) / KT * KT);
-  GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, b->KinvD, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG, nv};
-  ga.fail = b->fail;
   DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
   if (right_looking) ga.Cin = b->Lm;  // S lives (and is updated in place) in the lower tiles of Lm
   for (int j = 0; j < J; ++j) {
@@ -147,9 +153,11 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool r
                (int)b->n, (int)b->npad, J, nv};
   if ((rc = launch_solve(sa, count, st))) return rc;
   ++launches;
+  }
   if (prof) cudaEventRecord(b->ev[3], st);
   if (with_grad) {
     ga.Cin = nullptr;
+    ga.list = glist;
     gcount = ngrad;
     for (int i = 1; i < J; ++i) {
       ga.step = i; ga.mode = GEMM_TRTRI_ROW; ga.Cout = b->Lm;
@@ -160,7 +168,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool r
     if ((rc = gemm(ga, J * (J + 1) / 2))) return rc;
     ++launches;
     if (prof) cudaEventRecord(b->ev[4], st);
-    GradArgs gr{b->Xtptr, b->theta, b->A, b->KinvD, b->alpha, b->grad_part, b->grad, b->fail, list, ms, dstride,
+    GradArgs gr{b->Xtptr, b->theta, b->A, b->KinvD, b->alpha, b->grad_part, b->grad, b->fail, glist, ms, dstride,
                 (int)b->n, (int)b->npad, b->d, J, b->kind};
     if ((rc = launch_grad(gr, ngrad, st))) return rc;
     launches += 2;
@@ -169,20 +177,24 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, bool r
   return 0;
 }
 
-// One stream group of an evaluation pass: list[off .. off+count), the first ngrad of them with gradient.
-struct Group { int off, count, ngrad; bool rl; };
+// One stream group of an evaluation pass: list[off .. off+count), the first ngrad of them with gradient, the first
+// nreuse of those on the resident factorisation.
+struct Group { int off, count, ngrad, nreuse; bool rl; };
 
 // Order the active GPs of a pass into stream groups inside list_host: the value+gradient GPs and the value-only GPs
 // are each dealt evenly over the groups (equal work per stream), gradient GPs first inside every group.
-static std::vector<Group> build_groups(gprb_batch* b, const std::vector<int32_t>& grad_gps, const std::vector<int32_t>& val_gps) {
-  const int total = (int)(grad_gps.size() + val_gps.size());
+static std::vector<Group> build_groups(gprb_batch* b, const std::vector<int32_t>& reuse_gps, const std::vector<int32_t>& grad_gps,
+                                       const std::vector<int32_t>& val_gps) {
+  const int total = (int)(reuse_gps.size() + grad_gps.size() + val_gps.size());
   const int S = (b->profiling || total < 8 || total <= b->rl_max || b->nstreams == 1) ? 1 : b->nstreams;
   std::vector<Group> groups;
   int off = 0;
   for (int s = 0; s < S; ++s) {
+    const int r0 = (int)((int64_t)reuse_gps.size() * s / S), r1 = (int)((int64_t)reuse_gps.size() * (s + 1) / S);
     const int g0 = (int)((int64_t)grad_gps.size() * s / S), g1 = (int)((int64_t)grad_gps.size() * (s + 1) / S);
     const int v0 = (int)((int64_t)val_gps.size() * s / S), v1 = (int)((int64_t)val_gps.size() * (s + 1) / S);
-    Group g{off, (g1 - g0) + (v1 - v0), g1 - g0, !b->profiling && total <= b->rl_max};
+    Group g{off, (r1 - r0) + (g1 - g0) + (v1 - v0), (r1 - r0) + (g1 - g0), r1 - r0, !b->profiling && total <= b->rl_max};
+    for (int k = r0; k < r1; ++k) b->list_host[off++] = reuse_gps[k];
     for (int k = g0; k < g1; ++k) b->list_host[off++] = grad_gps[k];
     for (int k = v0; k < v1; ++k) b->list_host[off++] = val_gps[k];
     if (g.count > 0) groups.push_back(g);
@@ -197,7 +209,7 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
   if (groups.empty()) return 0;
   if (b->profiling) {
     const Group& g = groups[0];
-    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.rl, b->stream[0], true))) return rc;
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[0], true))) return rc;
     GPRB_CUDA(cudaStreamSynchronize(b->stream[0]));
     float ms = 0.f;
     const int last = g.ngrad > 0 ? 5 : 3;
@@ -223,7 +235,7 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
   for (size_t s = 0; s < groups.size(); ++s) {
     const Group& g = groups[s];
     if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(b->stream[s], b->join[0], 0));
-    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.rl, b->stream[s], false))) return rc;
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[s], false))) return rc;
     if (s > 0) {
       GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
       GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
@@ -235,24 +247,45 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
 // ONE pipeline pass over the GPs with mode != 0 (theta already on the device).  retry[gp] != 0: the GP's previous
 // pass failed its factorisation - its cumulative jitter grows by 1e-6 tr(K)/n (make_posdef!) instead of being reset.
 // Afterwards: info[gp] final for the GPs that are done, pending[gp] = 1 for those that need another retry pass.
-static int eval_pass(gprb_batch* b, const uint8_t* mode, const uint8_t* retry, std::vector<int32_t>& info,
-                     std::vector<uint8_t>& pending) {
+//
+// State reuse (theta_host != nullptr): a GP asked to evaluate, first try, at exactly the theta of its last successful
+// evaluation (same dataset upload) keeps what is resident - a value-only request is answered from the resident mll, a
+// gradient request only runs the inverse and the fused gradient on the resident factor (or nothing, when that gradient
+// is resident too).  The results are bit-identical to a fresh evaluation: every stage is deterministic, and the jitter
+// the earlier evaluation settled on is the one make_posdef! would arrive at again.  This is the optimiser's pattern:
+// the reference evaluates the point a line search accepts twice (value, then value + gradient), and once more after
+// the last iteration.
+static int eval_pass(gprb_batch* b, const double* theta_host, const uint8_t* mode, const uint8_t* retry,
+                     std::vector<int32_t>& info, std::vector<uint8_t>& pending) {
   int rc;
-  const int B = b->B;
+  const int B = b->B, P = b->P;
   if ((int)b->tries.size() != B) b->tries.assign(B, 0);
+  if ((int)b->theta_valid.size() != B) {
+    b->theta_valid.assign(B, 0); b->theta_last.assign((size_t)B * P, 0.0); b->info_last.assign(B, 0); b->ds_ver.assign(B, 0);
+  }
   pending.assign(B, 0);
-  std::vector<int32_t> grad_gps, val_gps;
+  static const bool allow_reuse = [] { const char* e = getenv("GPRB200_REUSE"); return !(e && e[0] == '0'); }();
+  std::vector<int32_t> reuse_gps, grad_gps, val_gps, cached;
   int nfresh = 0, nretry = 0;
   int32_t* aux = b->list_host + B;  // fresh GPs from the front, retried GPs from the back
   for (int i = 0; i < B; ++i) {
     if (!mode[i]) continue;
+    const bool is_retry = retry && retry[i];
+    if (allow_reuse && theta_host && !is_retry && !b->profiling && b->state_ok[i] && b->theta_valid[i] &&
+        b->ds_ver[i] == b->ds[i]->version &&
+        memcmp(theta_host + (size_t)i * P, b->theta_last.data() + (size_t)i * P, sizeof(double) * P) == 0) {
+      if (mode[i] == 1 || b->inv_ok[i]) cached.push_back(i);  // everything asked for is resident
+      else reuse_gps.push_back(i);                             // gradient on the resident factor
+      continue;
+    }
     (mode[i] == 2 ? grad_gps : val_gps).push_back(i);
-    if (retry && retry[i]) aux[B - 1 - nretry++] = i;
+    if (is_retry) aux[B - 1 - nretry++] = i;
     else { aux[nfresh++] = i; b->tries[i] = 0; }
   }
-  const int count = (int)(grad_gps.size() + val_gps.size());
+  for (int gp : cached) info[gp] = b->info_last[gp];
+  const int count = (int)(reuse_gps.size() + grad_gps.size() + val_gps.size());
   if (count == 0) return 0;
-  const std::vector<Group> groups = build_groups(b, grad_gps, val_gps);
+  const std::vector<Group> groups = build_groups(b, reuse_gps, grad_gps, val_gps);
   GPRB_CUDA(cudaMemcpyAsync(b->list, b->list_host, sizeof(int32_t) * 2 * B, cudaMemcpyHostToDevice, b->stream[0]));
   if (nfresh) {
     k_reset_jitter<<<(nfresh + 127) / 128, 128, 0, b->stream[0]>>>(b->jitter, b->list + B, nfresh);
@@ -268,9 +301,11 @@ static int eval_pass(gprb_batch* b, const uint8_t* mode, const uint8_t* retry, s
       if (mode[gp] && b->fail_host[gp] > 0) { sum += (double)b->fail_host[gp] / (double)b->n; ++nf; }
     if (nf) fprintf(stderr, "  pass: %d of %d factorisations failed, mean failing pivot at %.2f n\n", nf, count, sum / nf);
   }
+  for (int gp : reuse_gps) { info[gp] = b->info_last[gp]; b->inv_ok[gp] = 1; b->v_ok[gp] = 1; }
   for (int pass = 0; pass < 2; ++pass)
     for (int gp : (pass == 0 ? grad_gps : val_gps)) {
       const int f = b->fail_host[gp];
+      b->theta_valid[gp] = 0;
       if (f == 0) info[gp] = b->tries[gp];
       else if (f < 0) info[gp] = -2;
       else if (b->tries[gp] >= MAX_JITTER) info[gp] = -1;
@@ -278,17 +313,23 @@ static int eval_pass(gprb_batch* b, const uint8_t* mode, const uint8_t* retry, s
       b->state_ok[gp] = info[gp] >= 0;
       b->inv_ok[gp] = pass == 0 && info[gp] >= 0;
       b->v_ok[gp] = b->inv_ok[gp];
+      if (theta_host && info[gp] >= 0) {  // remember what is resident now
+        memcpy(b->theta_last.data() + (size_t)gp * P, theta_host + (size_t)gp * P, sizeof(double) * P);
+        b->theta_valid[gp] = 1;
+        b->info_last[gp] = info[gp];
+        b->ds_ver[gp] = b->ds[gp]->version;
+      }
     }
   return 0;
 }
 
 // Evaluation with the make_posdef! retry loop inside (gprb_eval / gprb_eval_mixed / gprb_eval_device): passes are
 // repeated for the GPs that still need a jitter until none is pending.
-static int evaluate_modes(gprb_batch* b, const uint8_t* mode, std::vector<int32_t>& info) {
+static int evaluate_modes(gprb_batch* b, const double* theta_host, const uint8_t* mode, std::vector<int32_t>& info) {
   info.assign(b->B, 0);
   std::vector<uint8_t> cur(mode, mode + b->B), retry(b->B, 0), pending;
   for (;;) {
-    int rc = eval_pass(b, cur.data(), retry.data(), info, pending);
+    int rc = eval_pass(b, theta_host, cur.data(), retry.data(), info, pending);
     if (rc) return rc;
     bool any = false;
     for (int i = 0; i < b->B; ++i) {
@@ -348,7 +389,7 @@ int eval_pass_host(gprb_batch* b, const double* theta, const uint8_t* mode, cons
   if (rc) return rc;
   std::vector<int32_t> info(b->B, 0);
   std::vector<uint8_t> pending;
-  if ((rc = eval_pass(b, mode, retry, info, pending))) return rc;
+  if ((rc = eval_pass(b, theta, mode, retry, info, pending))) return rc;
   memcpy(pending_out, pending.data(), b->B);
   return download_results(b, mode, info, pending_out, mll, grad, info_out);
 }
@@ -420,6 +461,7 @@ int64_t gprb_launch_count(gprb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 // ------------------------------------------------------------------------------------------------
 // Enqueue the host -> device copy of one dataset on `st` (no synchronisation).
 static int dataset_copy_async(gprb_dataset* ds, const double* X, int64_t ldx, cudaStream_t st) {
+  ds->version++;  // evaluations on the previous contents are no longer reusable
   if (ldx == ds->d)
     GPRB_CUDA(cudaMemcpyAsync(ds->X, X, sizeof(double) * ds->d * ds->n, cudaMemcpyHostToDevice, st));
   else
@@ -636,7 +678,7 @@ int gprb_eval_mixed(gprb_batch* b, const double* theta, const uint8_t* mode, dou
   int rc = upload_theta_rows(b, theta, act);
   if (rc) return rc;
   std::vector<int32_t> inf;
-  if ((rc = evaluate_modes(b, mode, inf))) return rc;
+  if ((rc = evaluate_modes(b, theta, mode, inf))) return rc;
   return download_results(b, mode, inf, nullptr, mll, grad, info);
 }
 
@@ -659,7 +701,7 @@ int gprb_eval_device(gprb_batch* b, const double* theta_dev, double* mll_dev, do
   GPRB_CUDA(cudaMemcpyAsync(b->theta, theta_dev, sizeof(double) * B * P, cudaMemcpyDeviceToDevice, b->stream[0]));
   std::vector<uint8_t> mode(B, grad_dev ? 2 : 1);
   std::vector<int32_t> inf;
-  int rc = evaluate_modes(b, mode.data(), inf);
+  int rc = evaluate_modes(b, nullptr, mode.data(), inf);  // theta lives on the device: nothing to compare, nothing remembered
   if (rc) return rc;
   GPRB_CUDA(cudaMemcpyAsync(mll_dev, b->mll, sizeof(double) * B, cudaMemcpyDeviceToDevice, b->stream[0]));
   if (grad_dev) GPRB_CUDA(cudaMemcpyAsync(grad_dev, b->grad, sizeof(double) * B * P, cudaMemcpyDeviceToDevice, b->stream[0]));

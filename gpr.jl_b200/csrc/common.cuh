@@ -61,6 +61,7 @@ struct gprb_dataset {
   int64_t npad = 0;      // n rounded up to a multiple of NB
   double* X = nullptr;   // device, d x n column-major (sample = contiguous column), tightly packed
   double* Xt = nullptr;  // device, Xt[p][npad]: one contiguous, zero-padded row per input dimension (TMA source)
+  uint64_t version = 0;  // bumped by every upload (state reuse compares it)
 };
 
 // Per-GP device state (structure-of-arrays over the batch), all resident in HBM:
@@ -108,6 +109,11 @@ struct gprb_batch {
   std::vector<uint8_t> state_ok;  // per GP: factor + alpha resident (last evaluation succeeded)
   std::vector<uint8_t> inv_ok;    // per GP: K^-1 resident in A (last evaluation was value+gradient)
   std::vector<uint8_t> v_ok;      // per GP: V = L^-T resident in the upper tiles of Lm (TRTRI stage done)
+  // state reuse (api.cu:eval_pass): theta / info / dataset version of the last successful host-theta evaluation per GP
+  std::vector<double> theta_last;
+  std::vector<uint8_t> theta_valid;
+  std::vector<int32_t> info_last;
+  std::vector<uint64_t> ds_ver;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // prediction scratch, allocated on first use and kept (grow-only): staged test inputs / prior means / outputs,
   // the right-hand-side block T [B][npad][PT] of the variance substitution and the per-block mean partials [B][J][PT]

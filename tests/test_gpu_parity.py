@@ -389,6 +389,54 @@ def test_mixed_value_and_gradient_pass(gprb):
                 batch.Kinv(b)  # value-only state holds no inverse
 
 
+def test_state_reuse_is_bit_identical_and_invalidated_by_uploads(gprb):
+    """A gradient request at the theta of the previous value-only evaluation (the optimiser's accepted point) runs on
+    the resident factor, a repeated request is answered from the resident results - both bit-identical to a fresh
+    evaluation; new targets / inputs invalidate the resident state."""
+    from gpr_jl_b200 import data
+    trials = [data.make_trial("CP", 200, seed=300 + t, n_test=3) for t in range(3)]
+    th = data.theta0("CP", trials[0]["X"])
+    th[1:-1] -= 1.0
+    rng = np.random.default_rng(11)
+    thetas = [np.tile(th, (4, 1)) + 0.05 * rng.standard_normal((4, th.size)) for _ in trials]
+    theta = np.concatenate(thetas)
+    fresh = build_batch(gprb, trials, thetas)
+    mll_f, grad_f, info_f = fresh.eval(theta=theta, grad=True)
+    ctx = gprb.gp.context()
+    batch = build_batch(gprb, trials, thetas)
+    mll_v, _, _ = batch.eval(theta=theta, grad=False)
+    l0 = ctx.launch_count()
+    mll_g, grad_g, info_g = batch.eval(theta=theta, grad=True)      # inverse + gradient only
+    l1 = ctx.launch_count()
+    mll_c, grad_c, info_c = batch.eval(theta=theta, grad=True)      # fully resident
+    l2 = ctx.launch_count()
+    assert np.array_equal(mll_v, mll_f) and np.array_equal(mll_g, mll_f) and np.array_equal(mll_c, mll_f)
+    assert np.array_equal(grad_g, grad_f) and np.array_equal(grad_c, grad_f)
+    assert np.array_equal(info_g, info_f) and np.array_equal(info_c, info_f)
+    assert l2 == l1 and 0 < l1 - l0 < 8                              # J = 2: one TRTRI row, LAUUM, gradient + reduce
+    mu_a, var_a = batch.predict_y(trials[0]["Xtest"])
+    mu_b, var_b = fresh.predict_y(trials[0]["Xtest"])
+    assert np.array_equal(mu_a, mu_b) and np.array_equal(var_a, var_b)
+    # a mixed pass: GPs 0-5 repeat their theta (value), GPs 6-11 move
+    theta2 = theta.copy()
+    theta2[6:] += 0.01
+    mode = np.array([1] * 6 + [2] * 6, dtype=np.uint8)
+    m2, g2, _ = batch.eval_mixed(theta2, mode)
+    m2f, g2f, _ = fresh.eval_mixed(theta2, np.full(12, 2, dtype=np.uint8))
+    assert np.array_equal(m2[:6], mll_f[:6]) and np.array_equal(m2, m2f) and np.array_equal(g2[6:], g2f[6:])
+    # new targets: same theta, different problem -> must be re-evaluated
+    ymm = batch.ymm.copy()
+    ymm[:, ::2] += 0.1
+    batch.update_data(ymm=ymm)
+    m3, _, _ = batch.eval(theta=theta2, grad=False)
+    assert not np.array_equal(m3, m2)
+    # new inputs through the batched upload
+    Xn = [tr["X"] * (1.0 + 1e-3) for tr in trials]
+    batch.update_data(trials_X=Xn)
+    m4, _, _ = batch.eval(theta=theta2, grad=False)
+    assert not np.array_equal(m4, m3)
+
+
 def test_multi_trial_batch_shares_datasets(gprb):
     from gpr_jl_b200 import data
     trials = data.make_config("CP", trials=3, n=200)
