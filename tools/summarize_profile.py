@@ -71,7 +71,12 @@ for rep in sorted(glob.glob(os.path.join(go, f"{tag}_gemm.ncu-rep")) + glob.glob
     if len(rr) < 3:
         continue
     h, u = rr[0], rr[1]
-    lines += ["", f"## `ncu --set full` : {os.path.basename(rep)}", ""]
+    legend = {"gemm": "tile GEMM: TRTRI_ROW rows 14 and 15, then the LAUUM launch (12 GPs)", "k0": "gradient tiles", "k1": "covariance assembly",
+              "k2": "diagonal-block factor", "k3": "substitution + mll", "k4": "predict: cross-covariances", "k5": "predict: finishing reduction",
+              "k6": "tile GEMM, Cholesky stage: CHOL_DIAG and CHOL_COL of block column 10 (tools/profile_extra.sh)",
+              "k7": "tile GEMM, predictive variance: one FWD_ROW launch, m = 100 test columns, 40 GPs of one stream group (tools/profile_extra.sh)"}
+    key = os.path.basename(rep)[len(tag) + 1:-len(".ncu-rep")]
+    lines += ["", f"## `ncu --set full` : {os.path.basename(rep)}" + (f" - {legend[key]}" if key in legend else ""), ""]
     for r in rr[2:]:
         name = r[h.index("Kernel Name")]
         lines.append(f"**{name}**")
