@@ -185,6 +185,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ["GPRB200_REUSE"] = "0"  # no resident-state reuse inside the benchmark: every step is a full evaluation
     import gpr_jl_b200 as G
     from gpr_jl_b200 import data
 
@@ -356,7 +357,7 @@ def main():
                        "evals_per_step": world * B,
                        "theta": ("config.json CP_MAX2048" if args.system == "CP" else "theta_0 of the config (data.CONFIGS)") + " + 0.1*N(0,I), fresh per step",
                        "l2": f"working set {2 * B * batch.n * batch.n * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
-                       "info_ok": info_ok, "parallelism": f"trial-sharded x{world}, per-step NCCL all-gather of results"},
+                       "info_ok": info_ok, "state_reuse": "off (GPRB200_REUSE=0; theta is fresh every step anyway)", "parallelism": f"trial-sharded x{world}, per-step NCCL all-gather of results"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "upload_ms_per_step": host_ms[0] / args.steps, "eval_ms_per_step": host_ms[1] / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
