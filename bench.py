@@ -119,6 +119,33 @@ class CpuArm:
         self.pool.join()
 
 
+def cpu_blas_arrangement(n_evals=2):
+    """Second arrangement SURVEY.md 8d asks for: ONE evaluation at a time with OpenBLAS on all host threads (what a single
+    Julia task with BLAS.set_num_threads(nproc) would do), evaluations in sequence.  -> (evals/s, threads)."""
+    from oracle import gp_oracle as go
+    import gpr_jl_b200  # noqa: F401
+    from gpr_jl_b200 import data
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    cores = os.cpu_count()
+    tr = data.make_config(SYSTEM, trials=1)[0]
+    X = np.ascontiguousarray(tr["X"].T)
+    thetas = data.perturbed_thetas(tr["theta0"][0], n_evals, seed=99)
+
+    def run():
+        go.eval_mll(X, tr["Y"][0], thetas[0], with_grad=True)  # warm-up
+        t0 = time.time()
+        for k in range(n_evals):
+            go.eval_mll(X, tr["Y"][k % 4], thetas[k + 1], with_grad=True)
+        return n_evals / (time.time() - t0)
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=cores):
+            return run(), cores
+    return run(), cores
+
+
 def julia_probe():
     """re-probe the reference's toolchain on the box the benchmark runs on (its own CPU path needs Julia)."""
     import shutil
@@ -146,6 +173,7 @@ def run_reference(args):
     arm.close()
     evals = args.steps * arm.cores
     v = evals / t_tot
+    blas_v, blas_threads = cpu_blas_arrangement()
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -153,7 +181,8 @@ def run_reference(args):
                        "sample": f"one step = {arm.cores} concurrent logML+gradient evaluations (one n=2000 GP per host core)"},
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": arm.cores, "kind": "port",
                              "sample": f"{evals} evaluations of n=2000,d=26 GPs, {arm.cores} worker processes x 1 BLAS thread (oracle: restated "
-                                       f"GaussianProcesses.jl path on scipy OpenBLAS; julia on this box: {julia_probe()}; trials in parallel like core.jl:28)"},
+                                       f"GaussianProcesses.jl path on scipy OpenBLAS; julia on this box: {julia_probe()}; trials in parallel like core.jl:28)",
+                             "arrangements": {f"{arm.cores} processes x 1 BLAS thread": v, f"1 process x {blas_threads} BLAS threads": blas_v}},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -170,6 +199,9 @@ def main():
                     help="BASELINE config family (default CP, the one the metric is quoted on); FB = d=52, 12 GPs per trial")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-predict", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, what the driver runs): every rank owns --trials trials; strong: the SAME --trials "
+                         "trials (north_star: '100 trial datasets batched across 8xB200') are split round-robin over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -189,8 +221,17 @@ def main():
     import gpr_jl_b200 as G
     from gpr_jl_b200 import data
 
-    n, T = args.n, args.trials
-    trials = data.make_config(args.system, trials=T, n=n, first_trial=rank * T)
+    from gpr_jl_b200 import shard
+    n = args.n
+    if args.scaling == "strong":  # the same T trials for every world size, trial t on rank t mod world (core.jl:28's jobid axis)
+        mine = shard.trials_for_rank(args.trials, rank, world)
+        trials = [data.make_config(args.system, trials=1, n=n, first_trial=t)[0] for t in mine]
+        T_total = args.trials
+    else:
+        trials = data.make_config(args.system, trials=args.trials, n=n, first_trial=rank * args.trials)
+        mine = [rank * args.trials + t for t in range(args.trials)]
+        T_total = world * args.trials
+    T = len(trials)
     G_out = trials[0]["Y"].shape[0]
     d = trials[0]["X"].shape[0]
     gps = []
@@ -200,6 +241,7 @@ def main():
             gps.append(G.GPE(tr["X"], tr["Y"][k], G.MeanZero(), G.SEArd(th[1:-1], th[-1]), logNoise=th[0]))
     batch = G.GPBatch(gps)
     B, P = batch.B, batch.P
+    B_total = T_total * G_out  # GPs evaluated per step by the whole job
     theta0 = batch.get_params()
     nsets = args.steps + args.warmup
     thetas = data.perturbed_thetas(theta0, nsets, seed=1234 + rank)
@@ -209,13 +251,17 @@ def main():
     mll_dev = torch.empty(B, dtype=torch.float64, device=dev)
     grad_dev = torch.empty(B, P, dtype=torch.float64, device=dev)
     info_dev = torch.empty(B, dtype=torch.int32, device=dev)
-    gathered = [torch.empty(B, P + 1, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    Bmax = -(-args.trials // world) * G_out if args.scaling == "strong" else B  # padded per-rank rows of the device gather
+    gathered = [torch.empty(Bmax, P + 1, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    send = torch.zeros(Bmax, P + 1, dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream()
 
     def step_device(i):
         batch.eval_device(th_dev[i].data_ptr(), mll_dev.data_ptr(), grad_dev.data_ptr(), info_dev.data_ptr(), stream.cuda_stream)
         if world > 1:  # final gather of per-GP results over NVLink (latency-bound, a few hundred KB)
-            dist.all_gather(gathered, torch.cat([mll_dev[:, None], grad_dev], dim=1))
+            send[:B, 0] = mll_dev
+            send[:B, 1:] = grad_dev
+            dist.all_gather(gathered, send)
 
     def barrier():
         if world > 1:
@@ -223,6 +269,8 @@ def main():
         torch.cuda.synchronize()
 
     ctx = G.gp.context()
+    if world > 1:
+        ctx.comm_init(rank, world)  # the library's own NCCL communicator (gprb_comm_init_rank) for gprb_gather in the e2e leg
     for w in range(args.warmup):
         step_device(w)
     barrier()
@@ -242,8 +290,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     sampler.stop_flag = True
-    info_ok = int((info_dev >= 0).sum().item())
-    value = world * B * args.steps / (ms_total * 1e-3)
+    info_host = info_dev.cpu().numpy()
+    info_hist = {str(int(k)): int(c) for k, c in zip(*np.unique(info_host, return_counts=True))}  # rank 0, last timed step
+    value = B_total * args.steps / (ms_total * 1e-3)
 
     # ---- value-only evaluations (the optimiser's line-search trials: assembly + Cholesky + solve), device resident
     v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,7 +306,7 @@ def main():
     msv = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(msv, op=dist.ReduceOp.MAX)
-    value_only = world * B * args.steps / (float(msv.item()) * 1e-3)
+    value_only = B_total * args.steps / (float(msv.item()) * 1e-3)
 
     # ---- e2e: public API with host buffers; X, y, theta go up and mll, grad come back every step
     # host inputs live in page-locked memory (the copies inside the timed region are then real async DMA transfers)
@@ -273,6 +322,10 @@ def main():
         batch.update_data(Xs, ymm)
         t_b = time.perf_counter()
         out = batch.eval(theta=thetas[i], grad=True)
+        if world > 1:  # the path's one collective: per-trial result rows to every rank (gprb_gather: ncclAllGather in the .so)
+            rows = {mine[t]: np.concatenate([out[0][t * G_out:(t + 1) * G_out], out[1][t * G_out:(t + 1) * G_out].ravel()])
+                    for t in range(T)}
+            ctx.gather(rows, T_total, G_out * (P + 1))
         host_ms[0] += (t_b - t_a) * 1e3
         host_ms[1] += (time.perf_counter() - t_b) * 1e3
         return out
@@ -286,9 +339,41 @@ def main():
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(dt.item())
-    h2d = T * d * n * 8 + B * n * 8 + B * P * 8
-    d2h = B * 8 + B * P * 8 + B * 4
+    e2e_value = B_total * args.steps / float(dt.item())
+    h2d = T_total * d * n * 8 + B_total * n * 8 + B_total * P * 8  # whole job: X, y - m, theta of every GP, every step
+    d2h = B_total * 8 + B_total * P * 8 + B_total * 4
+
+    # ---- prediction throughput (second half of the BASELINE metric): 100 test states per GP (the 100 test states of a
+    # trial, predictdynamics.jl:11-19), mean + variance and mean only, through gprb_predict with host buffers; device time
+    # from CUDA events on the library's prediction stream (H2D of the states and D2H of mu/var included), max over ranks
+    pred = None
+    if not args.no_predict:
+        m, reps = 100, 10
+        Xt = data.make_trial(args.system, 8, seed=99, n_test=m)["Xtest"]
+        pm = {}
+        for key, want_var in (("mean_var", True), ("mean_only", False)):
+            for _ in range(2):
+                batch.predict_y(Xt, var=want_var)
+            barrier()
+            tdev, t0 = 0.0, time.perf_counter()
+            for _ in range(reps):
+                batch.predict_y(Xt, var=want_var)
+                tdev += batch.last_predict_ms(0)
+            twall = time.perf_counter() - t0
+            tt = torch.tensor([tdev * 1e-3, twall], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            pm[key] = (float(tt[0].item()) / reps, float(tt[1].item()) / reps)
+        f_pred = n ** 2 + (3 * d + 4) * n  # variance n^2 + mean (3d+4) n flops per sample
+        pk, _ = fp64_peak()
+        sps = B_total * m / pm["mean_var"][0]
+        pred = {"samples_per_s_mean_var": sps, "samples_per_s_mean_only": B_total * m / pm["mean_only"][0],
+                "e2e_samples_per_s_mean_var": B_total * m / pm["mean_var"][1], "e2e_samples_per_s_mean_only": B_total * m / pm["mean_only"][1],
+                "m": m, "B": B_total, "reps": reps,
+                "roofline": {"bound": "tensor", "kernel": "k_tile_gemm FWD_ROW (L^-1 K*, fp64 DMMA) + k_predict_cross", "achieved": f_pred * sps / 1e12,
+                             "peak": pk * world, "unit": "TFLOP/s", "frac": f_pred * sps / 1e12 / (pk * world),
+                             "flops_per_sample": f_pred},
+                "note": "gprb_predict with host buffers; timed with CUDA events on the library's stream (copies included), max over ranks"}
 
     if rank != 0:
         if world > 1:
@@ -316,26 +401,7 @@ def main():
             "launches_per_step": int(st["gemm_launches"]), "flops_per_launch": gemm_flops / max(st["gemm_launches"], 1),
             "avg_launch_ms": st["gemm"] / max(st["gemm_launches"], 1),
             "stage_ms": {k: round(v, 3) for k, v in st.items() if k != "gemm_launches"},
-            "whole_eval_frac_of_peak": (flops_eval(n, d) * B * args.steps / (ms_total * 1e-3) / 1e12) / peak}
-
-    # ---- prediction throughput (second half of the BASELINE metric): 100 test states per GP, mean + variance
-    pred = None
-    if not args.no_predict:
-        m = 100
-        Xt = data.make_trial(args.system, 8, seed=99, n_test=m)["Xtest"]
-        batch.predict_y(Xt, var=True)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        reps = 2
-        for _ in range(reps):
-            batch.predict_y(Xt, var=True)
-        tp = (time.perf_counter() - t0) / reps
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            batch.predict_y(Xt, var=False)
-        tm = (time.perf_counter() - t0) / reps
-        pred = {"samples_per_s_mean_var": B * m / tp, "samples_per_s_mean_only": B * m / tm, "m": m, "B": B,
-                "note": "through gprb_predict with host buffers (e2e), one GPU"}
+            "whole_eval_frac_of_peak": (flops_eval(n, d) * B_total * args.steps / (ms_total * 1e-3) / 1e12) / (peak * world)}
 
     cpu = None
     if world == 1 and args.cpu_seconds > 0:  # bounded sample: rounds of `cores` concurrent evaluations until ~cpu_seconds of wall time
@@ -346,18 +412,26 @@ def main():
             dt_cpu += arm.round()[0]
             rounds += 1
         arm.close()
+        blas_v, blas_threads = cpu_blas_arrangement()
         cpu = {"value": rounds * arm.cores / dt_cpu, "unit": "evals/s", "cores": arm.cores, "kind": "port",
+               "arrangements": {f"{arm.cores} processes x 1 BLAS thread": rounds * arm.cores / dt_cpu,
+                                f"1 process x {blas_threads} BLAS threads": blas_v},
                "sample": f"{rounds * arm.cores} logML+gradient evaluations of n={N_TRAIN},d=26 GPs in {dt_cpu:.1f} s ({rounds} rounds after one warm-up "
                          f"round), {arm.cores} worker processes x 1 BLAS thread (oracle: restated GaussianProcesses.jl path on scipy OpenBLAS, "
                          "trials in parallel like core.jl:28)"}
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD_NAMES[args.system]}, n={n}, d={d}, G={G_out} GPs/trial, {T} trials (B={B} GPs per GPU)",
-                       "evals_per_step": world * B,
+            "config": {"workload": f"{WORKLOAD_NAMES[args.system]}, n={n}, d={d}, G={G_out} GPs/trial, {args.trials} trials (B={args.trials * G_out} GPs per GPU)"
+                                   if args.scaling == "weak" else
+                                   f"{WORKLOAD_NAMES[args.system]}, n={n}, d={d}, G={G_out} GPs/trial, {args.trials} trials in total split over {world} GPUs (B={B} GPs on rank 0)",
+                       "evals_per_step": B_total,
                        "theta": ("config.json CP_MAX2048" if args.system == "CP" else "theta_0 of the config (data.CONFIGS)") + " + 0.1*N(0,I), fresh per step",
                        "l2": f"working set {2 * B * batch.n * batch.n * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
-                       "info_ok": info_ok, "state_reuse": "off (GPRB200_REUSE=0; theta is fresh every step anyway)", "parallelism": f"trial-sharded x{world}, per-step NCCL all-gather of results"},
+                       "info_histogram": info_hist,
+                       "info_histogram_note": "per-GP make_posdef! status of rank 0's GPs at the last timed step: key = jitter additions needed "
+                                              "(0 = factorised first try), -1 = not PD after 10, -2 = non-finite theta; retried GPs run extra passes inside the timed step",
+                       "state_reuse": "off (GPRB200_REUSE=0; theta is fresh every step anyway)", "parallelism": f"trial-sharded x{world} ({args.scaling}), per-step NCCL all-gather of results (e2e leg: gprb_gather inside libgprb200.so)"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "upload_ms_per_step": host_ms[0] / args.steps, "eval_ms_per_step": host_ms[1] / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,

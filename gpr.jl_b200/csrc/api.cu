@@ -21,9 +21,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return e == cudaErrorMemoryAllocation ? GPRB_ERR_NOMEM : GPRB_ERR_CUDA;
 }
 
-__global__ void k_reset_jitter(double* jitter, const int32_t* list, int count) {
+// fresh evaluation: the diagonal term starts at the GP's fixed offset (gprb_batch_set_diag_offset, default 0)
+__global__ void k_reset_jitter(double* jitter, const double* diag_off, const int32_t* list, int count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < count) jitter[list[k]] = 0.0;
+  if (k < count) jitter[list[k]] = diag_off[list[k]];
 }
 
 template <typename T>
@@ -38,10 +39,18 @@ static int dev_alloc(T** p, size_t count) {
 static void free_batch(gprb_batch* b) {
   if (!b) return;
   cudaFree(b->Xptr); cudaFree(b->Xtptr); cudaFree(b->ymm); cudaFree(b->theta); cudaFree(b->A); cudaFree(b->Lm);
-  cudaFree(b->Dinv); cudaFree(b->DinvT); cudaFree(b->KinvD); cudaFree(b->alpha); cudaFree(b->zbuf); cudaFree(b->jitter);
+  cudaFree(b->Dinv); cudaFree(b->DinvT); cudaFree(b->KinvD); cudaFree(b->alpha); cudaFree(b->zbuf); cudaFree(b->jitter); cudaFree(b->diag_off);
   cudaFree(b->logdet_part); cudaFree(b->fail); cudaFree(b->mll); cudaFree(b->grad);
   cudaFree(b->grad_part); cudaFree(b->list);
-  cudaFree(b->pX); cudaFree(b->pms); cudaFree(b->pmu); cudaFree(b->pvar); cudaFree(b->pT); cudaFree(b->pmupart);
+  for (gprb_predict_slot& sl : b->ps) {
+    cudaFree(sl.pX); cudaFree(sl.pms); cudaFree(sl.pmu); cudaFree(sl.pvar); cudaFree(sl.pT); cudaFree(sl.pmupart);
+    cudaFree(sl.pq); cudaFree(sl.pcount); cudaFree(sl.mask);
+    if (sl.h_in) cudaFreeHost(sl.h_in);
+    if (sl.h_out) cudaFreeHost(sl.h_out);
+    if (sl.h_mask) cudaFreeHost(sl.h_mask);
+    if (sl.t0) cudaEventDestroy(sl.t0);
+    if (sl.t1) cudaEventDestroy(sl.t1);
+  }
   if (b->list_host) cudaFreeHost(b->list_host);
   if (b->fail_host) cudaFreeHost(b->fail_host);
   if (b->stage_host) cudaFreeHost(b->stage_host);
@@ -288,7 +297,7 @@ static int eval_pass(gprb_batch* b, const double* theta_host, const uint8_t* mod
   const std::vector<Group> groups = build_groups(b, reuse_gps, grad_gps, val_gps);
   GPRB_CUDA(cudaMemcpyAsync(b->list, b->list_host, sizeof(int32_t) * 2 * B, cudaMemcpyHostToDevice, b->stream[0]));
   if (nfresh) {
-    k_reset_jitter<<<(nfresh + 127) / 128, 128, 0, b->stream[0]>>>(b->jitter, b->list + B, nfresh);
+    k_reset_jitter<<<(nfresh + 127) / 128, 128, 0, b->stream[0]>>>(b->jitter, b->diag_off, b->list + B, nfresh);
     GPRB_CUDA(cudaGetLastError());
   }
   if (nretry && (rc = launch_add_jitter(b->theta, b->jitter, b->list + 2 * B - nretry, b->d, nretry, b->stream[0]))) return rc;
@@ -400,7 +409,7 @@ using namespace gprb;
 
 extern "C" {
 
-int gprb_version(void) { return 100; }
+int gprb_version(void) { return 200; }
 const char* gprb_last_error(void) { return g_err.c_str(); }
 
 int gprb_init(gprb_ctx** out, int device) {
@@ -420,6 +429,10 @@ int gprb_init(gprb_ctx** out, int device) {
     return GPRB_ERR_NODEVICE;
   }
   GPRB_CUDA(cudaSetDevice(device));
+  // dynamic shared-memory opt-ins are per-device function attributes: set them for THIS device (a second context on
+  // another GPU of the same process gets its own)
+  int rc;
+  if ((rc = configure_tile_gemm()) || (rc = configure_diag_factor())) return rc;
   gprb_ctx* c = new (std::nothrow) gprb_ctx();
   GPRB_REQUIRE(c != nullptr, "gprb_init: out of host memory");
   c->device = device;
@@ -439,6 +452,7 @@ int gprb_init(gprb_ctx** out, int device) {
 int gprb_destroy(gprb_ctx* ctx) {
   if (ctx) {
     cudaSetDevice(ctx->device);
+    comm_release(ctx);
     if (ctx->upload) cudaStreamDestroy(ctx->upload);
     if (ctx->upload2) cudaStreamDestroy(ctx->upload2);
     if (ctx->upload_ev) cudaEventDestroy(ctx->upload_ev);
@@ -515,6 +529,70 @@ int gprb_dataset_update(gprb_dataset* ds, const double* X, int64_t ldx) {
   return dataset_upload(ds, X, ldx);
 }
 
+// ds[0 .. count) are the members 0 .. count-1 of one slab, in order, and the host matrices form one contiguous block:
+// the whole upload is ONE host->device copy and ONE transpose launch (the per-dataset form costs the host ~10 us per
+// copy / launch to enqueue - 1 ms per 100 trial datasets, which no overlap on the device hides).
+static bool slab_contiguous(int32_t count, gprb_dataset* const* ds, const double* const* X, int64_t ldx) {
+  if (count < 1 || !ds[0]->slab || ds[0]->slab->count != count || ldx != ds[0]->d) return false;
+  for (int i = 0; i < count; ++i) {
+    if (ds[i]->slab != ds[0]->slab || ds[i]->slab_index != i) return false;
+    if (X[i] != X[0] + (int64_t)i * ds[0]->n * ldx) return false;
+  }
+  return true;
+}
+
+static int slab_upload(gprb_ctx* ctx, int32_t count, gprb_dataset* const* ds, const double* X0) {
+  gprb_slab* sl = ds[0]->slab;
+  const int64_t n = ds[0]->n, npad = ds[0]->npad;
+  const int d = ds[0]->d;
+  for (int i = 0; i < count; ++i) ds[i]->version++;
+  GPRB_CUDA(cudaMemcpyAsync(sl->X, X0, sizeof(double) * (size_t)count * n * d, cudaMemcpyHostToDevice, ctx->upload));
+  int rc = launch_transpose_inputs_batched(sl->X, sl->Xt, (int)n, (int)npad, d, count, ctx->upload);
+  if (rc) return rc;
+  ctx->launches++;
+  GPRB_CUDA(cudaStreamSynchronize(ctx->upload));
+  return 0;
+}
+
+int gprb_datasets_create(gprb_ctx* ctx, int32_t count, int64_t n, int32_t d, const double* const* X, int64_t ldx,
+                         gprb_dataset** out) {
+  GPRB_REQUIRE(ctx && X && out && count >= 1, "gprb_datasets_create: bad argument");
+  GPRB_REQUIRE(n >= 1 && n <= (1 << 20), "gprb_datasets_create: n out of range");
+  GPRB_REQUIRE(d >= 1 && d <= MAX_D, "gprb_datasets_create: d must be in 1..62");
+  GPRB_REQUIRE(ldx >= d, "gprb_datasets_create: ldx < d");
+  for (int i = 0; i < count; ++i) { GPRB_REQUIRE(X[i] != nullptr, "gprb_datasets_create: NULL matrix"); out[i] = nullptr; }
+  GPRB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t npad = (n + NB - 1) / NB * NB;
+  gprb_slab* sl = new (std::nothrow) gprb_slab();
+  GPRB_REQUIRE(sl != nullptr, "gprb_datasets_create: out of host memory");
+  int rc;
+  if ((rc = dev_alloc(&sl->X, (size_t)count * n * d)) || (rc = dev_alloc(&sl->Xt, (size_t)count * npad * d))) {
+    cudaFree(sl->X); cudaFree(sl->Xt); delete sl;
+    return rc;
+  }
+  sl->count = count; sl->refs = count;
+  for (int i = 0; i < count; ++i) {
+    gprb_dataset* ds = new (std::nothrow) gprb_dataset();
+    if (!ds) {  // unwind
+      for (int k = 0; k < i; ++k) { delete out[k]; out[k] = nullptr; }
+      cudaFree(sl->X); cudaFree(sl->Xt); delete sl;
+      set_error("gprb_datasets_create: out of host memory");
+      return GPRB_ERR_ARG;
+    }
+    ds->ctx = ctx; ds->n = n; ds->d = d; ds->npad = npad;
+    ds->X = sl->X + (size_t)i * n * d;
+    ds->Xt = sl->Xt + (size_t)i * npad * d;
+    ds->slab = sl; ds->slab_index = i;
+    out[i] = ds;
+  }
+  rc = gprb_datasets_update(ctx, count, out, X, ldx);
+  if (rc) {
+    for (int i = 0; i < count; ++i) { delete out[i]; out[i] = nullptr; }
+    cudaFree(sl->X); cudaFree(sl->Xt); delete sl;
+  }
+  return rc;
+}
+
 int gprb_datasets_update(gprb_ctx* ctx, int32_t count, gprb_dataset* const* ds, const double* const* X, int64_t ldx) {
   GPRB_REQUIRE(ctx && ds && X && count >= 0, "gprb_datasets_update: bad argument");
   for (int i = 0; i < count; ++i) {
@@ -523,6 +601,7 @@ int gprb_datasets_update(gprb_ctx* ctx, int32_t count, gprb_dataset* const* ds, 
     GPRB_REQUIRE(ldx >= ds[i]->d, "gprb_datasets_update: ldx < d");
   }
   GPRB_CUDA(cudaSetDevice(ctx->device));
+  if (slab_contiguous(count, ds, X, ldx)) return slab_upload(ctx, count, ds, X[0]);
   // The copies are queued back to back on the upload stream (truly asynchronous when the host matrices are page-locked);
   // the transposes run on a second stream, a quarter of the datasets at a time, behind an event - a transpose between
   // two copies on one stream would stall the copy engine for a kernel launch each time (2.6 -> 1.4 ms per 100 datasets).
@@ -549,7 +628,15 @@ int gprb_datasets_update(gprb_ctx* ctx, int32_t count, gprb_dataset* const* ds, 
 
 int gprb_dataset_destroy(gprb_dataset* ds) {
   if (!ds) return GPRB_OK;
-  cudaFree(ds->X); cudaFree(ds->Xt);
+  if (ds->slab) {
+    if (--ds->slab->refs == 0) {
+      cudaSetDevice(ds->ctx->device);
+      cudaFree(ds->slab->X); cudaFree(ds->slab->Xt);
+      delete ds->slab;
+    }
+  } else {
+    cudaFree(ds->X); cudaFree(ds->Xt);
+  }
   delete ds;
   return GPRB_OK;
 }
@@ -590,7 +677,7 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
         (rc = dev_alloc(&b->theta, (size_t)B * b->P)) || (rc = dev_alloc(&b->A, mat * B)) || (rc = dev_alloc(&b->Lm, mat * B)) ||
         (rc = dev_alloc(&b->Dinv, dinv * B)) || (rc = dev_alloc(&b->DinvT, dinv * B)) || (rc = dev_alloc(&b->KinvD, dinv * B)) ||
         (rc = dev_alloc(&b->alpha, (size_t)B * b->npad)) || (rc = dev_alloc(&b->zbuf, (size_t)B * b->npad)) ||
-        (rc = dev_alloc(&b->jitter, B)) || (rc = dev_alloc(&b->logdet_part, (size_t)B * b->J)) ||
+        (rc = dev_alloc(&b->jitter, B)) || (rc = dev_alloc(&b->diag_off, B)) || (rc = dev_alloc(&b->logdet_part, (size_t)B * b->J)) ||
         (rc = dev_alloc(&b->fail, B)) || (rc = dev_alloc(&b->mll, B)) || (rc = dev_alloc(&b->grad, (size_t)B * b->P)) ||
         (rc = dev_alloc(&b->grad_part, (size_t)B * ntiles * GRAD_PARTS_PER_TILE * b->P)) || (rc = dev_alloc(&b->list, 2 * (size_t)B)))
       break;
@@ -620,6 +707,7 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
         (e = cudaMemcpy(b->Xtptr, xtp.data(), sizeof(double*) * B, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemset(b->theta, 0, sizeof(double) * B * b->P)) != cudaSuccess ||
         (e = cudaMemset(b->jitter, 0, sizeof(double) * B)) != cudaSuccess ||
+        (e = cudaMemset(b->diag_off, 0, sizeof(double) * B)) != cudaSuccess ||
         (e = cudaMemset(b->ymm, 0, sizeof(double) * b->npad * B)) != cudaSuccess ||  // zero padding, written once
         (e = cudaMemset(b->fail, 0, sizeof(int32_t) * B)) != cudaSuccess) {
       rc = cuda_fail(e, "batch init copies", __FILE__, __LINE__);
@@ -636,6 +724,21 @@ int gprb_batch_set_targets(gprb_batch* b, const double* ymm) {
   GPRB_REQUIRE(b && ymm, "gprb_batch_set_targets: NULL argument");
   GPRB_CUDA(cudaSetDevice(b->ctx->device));
   return upload_targets(b, ymm);
+}
+
+int gprb_batch_set_diag_offset(gprb_batch* b, const double* offset) {
+  GPRB_REQUIRE(b, "gprb_batch_set_diag_offset: NULL batch");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  if (offset) {
+    for (int i = 0; i < b->B; ++i) GPRB_REQUIRE(isfinite(offset[i]), "gprb_batch_set_diag_offset: non-finite offset");
+    GPRB_CUDA(cudaMemcpy(b->diag_off, offset, sizeof(double) * b->B, cudaMemcpyHostToDevice));
+  } else {
+    GPRB_CUDA(cudaMemset(b->diag_off, 0, sizeof(double) * b->B));
+  }
+  // a different matrix is factorised from now on: nothing resident may be reused
+  b->state_ok.assign(b->B, 0); b->inv_ok.assign(b->B, 0); b->v_ok.assign(b->B, 0);
+  std::fill(b->theta_valid.begin(), b->theta_valid.end(), (uint8_t)0);
+  return GPRB_OK;
 }
 
 int gprb_batch_destroy(gprb_batch* b) {
@@ -716,88 +819,191 @@ int gprb_eval_device(gprb_batch* b, const double* theta_dev, double* mll_dev, do
 }
 
 // ------------------------------------------------------------------------------------------------
-static int ensure_doubles(double** p, size_t* cap, size_t need) {
+}  // extern "C"
+
+template <typename T>
+static int ensure_dev(T** p, size_t* cap, size_t need, bool zero = false) {
   if (*p && *cap >= need) return 0;
   cudaFree(*p);
   *p = nullptr; *cap = 0;
   int rc = dev_alloc(p, need);
-  if (!rc) *cap = need;
-  return rc;
+  if (rc) return rc;
+  if (zero) GPRB_CUDA(cudaMemset(*p, 0, sizeof(T) * need));
+  *cap = need;
+  return 0;
 }
 
-int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_stride, const double* mstar, double* mu,
-                 double* var) {
-  GPRB_REQUIRE(b && Xstar && mu, "gprb_predict: NULL argument");
-  GPRB_REQUIRE(m >= 1 && m <= (1 << 24), "gprb_predict: m out of range");
-  for (int i = 0; i < b->B; ++i)
-    GPRB_REQUIRE(b->state_ok[i], "gprb_predict: a GP has no evaluated state - call gprb_eval or gprb_optimize first");
-  GPRB_REQUIRE(xstar_stride == 0 || xstar_stride >= m * b->d, "gprb_predict: xstar_stride must be 0 or >= d*m");
-  GPRB_CUDA(cudaSetDevice(b->ctx->device));
-  const int B = b->B, J = b->J;
-  cudaStream_t st = b->stream[0];
-  const size_t nx = (size_t)(xstar_stride ? xstar_stride * (B - 1) + m * b->d : m * b->d);
+static int ensure_pinned(double** p, size_t* cap, size_t need) {
+  if (*p && *cap >= need) return 0;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr; *cap = 0;
+  cudaError_t e = cudaMallocHost((void**)p, sizeof(double) * std::max<size_t>(need, 1));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(predict staging)", __FILE__, __LINE__);
+  *cap = need;
+  return 0;
+}
+
+// Enqueue the prediction of the GPs gp0 .. gp1-1 on pipeline `slot` (streams 4 slot .. 4 slot + 3): inputs are copied to
+// the slot's pinned staging, everything else is asynchronous; predict_collect waits and hands the results out.
+static int predict_enqueue(gprb_batch* b, int slot, int gp0, int gp1, int64_t m, const double* Xstar, int64_t xstar_stride,
+                           const double* mstar, bool want_var, int gpb = 1) {
+  gprb_predict_slot& sl = b->ps[slot];
+  const int B = b->B, J = b->J, count = gp1 - gp0;
+  cudaStream_t* str = b->stream + 4 * slot;
+  cudaStream_t st = str[0];
+  const int nblocks = (count + gpb - 1) / gpb;  // Xstar blocks: one per gpb consecutive GPs (the outputs of a trial)
+  const size_t nx = (size_t)(xstar_stride ? xstar_stride * (nblocks - 1) + m * b->d : m * b->d);
+  const size_t nout = (size_t)count * m;
   int rc;
-  if ((rc = ensure_doubles(&b->pX, &b->pX_cap, nx)) || (rc = ensure_doubles(&b->pmu, &b->pmu_cap, (size_t)B * m))) return rc;
-  if (mstar && (rc = ensure_doubles(&b->pms, &b->pms_cap, (size_t)B * m))) return rc;
-  if (var && (rc = ensure_doubles(&b->pvar, &b->pvar_cap, (size_t)B * m))) return rc;
-  GPRB_CUDA(cudaMemcpyAsync(b->pX, Xstar, sizeof(double) * nx, cudaMemcpyHostToDevice, st));
-  if (mstar) GPRB_CUDA(cudaMemcpyAsync(b->pms, mstar, sizeof(double) * B * m, cudaMemcpyHostToDevice, st));
+  if (!sl.t0) {
+    GPRB_CUDA(cudaEventCreate(&sl.t0));
+    GPRB_CUDA(cudaEventCreate(&sl.t1));
+    GPRB_CUDA(cudaMallocHost((void**)&sl.h_mask, sizeof(int32_t) * B));
+    if ((rc = dev_alloc(&sl.mask, (size_t)B))) return rc;
+  }
+  if ((rc = ensure_dev(&sl.pX, &sl.pX_cap, nx)) || (rc = ensure_dev(&sl.pmu, &sl.pmu_cap, nout)) ||
+      (rc = ensure_pinned(&sl.h_in, &sl.h_in_cap, nx + (mstar ? nout : 0))) ||
+      (rc = ensure_pinned(&sl.h_out, &sl.h_out_cap, 2 * nout)))
+    return rc;
+  if (mstar && (rc = ensure_dev(&sl.pms, &sl.pms_cap, nout))) return rc;
+  if (want_var && (rc = ensure_dev(&sl.pvar, &sl.pvar_cap, nout))) return rc;
+  // per-GP mask: a GP without an evaluated state gets NaN rows and blocks nobody (examples/parallel/core.jl:41-46)
+  bool all_v = true, any_ok = false;
+  for (int i = 0; i < B; ++i) sl.h_mask[i] = b->state_ok[i] ? 0 : 1;
+  for (int i = gp0; i < gp1; ++i)
+    if (b->state_ok[i]) { any_ok = true; all_v = all_v && b->v_ok[i]; }
+  memcpy(sl.h_in, Xstar, sizeof(double) * nx);
+  if (mstar) memcpy(sl.h_in + nx, mstar, sizeof(double) * nout);
+  GPRB_CUDA(cudaEventRecord(sl.t0, st));
+  GPRB_CUDA(cudaMemcpyAsync(sl.mask, sl.h_mask, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  GPRB_CUDA(cudaMemcpyAsync(sl.pX, sl.h_in, sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+  if (mstar) GPRB_CUDA(cudaMemcpyAsync(sl.pms, sl.h_in + nx, sizeof(double) * nout, cudaMemcpyHostToDevice, st));
 
   // GEMV-like path: few test columns and the triangular inverse already resident (the last evaluation had a gradient)
-  bool all_v = true;
-  for (int i = 0; i < B; ++i) all_v = all_v && b->v_ok[i];
-  const size_t small_smem = ((size_t)8 * b->npad + 8 * MAX_D + MAX_D + 8) * sizeof(double);
-  if (var && m <= 8 && all_v && small_smem <= 227 * 1024) {
-    PredictArgs pa{b->Xptr, b->theta, b->alpha, b->Lm, b->DinvT, b->pX, mstar ? b->pms : nullptr, b->pmu, b->pvar,
-                   xstar_stride, b->npad * b->npad, (int64_t)J * NB * NB, (int)b->n, (int)b->npad, b->d, (int)m, b->kind};
-    if ((rc = launch_predict(pa, B, st))) return rc;
+  const int ps = m <= 1 ? 1 : m <= 2 ? 2 : m <= 4 ? 4 : 8;
+  const size_t small_smem = ((size_t)ps * b->npad + ps * MAX_D + MAX_D + 8) * sizeof(double);
+  if (want_var && m <= 8 && all_v && any_ok && small_smem <= 227 * 1024) {
+    const int ncc = (int)((m + ps - 1) / ps);
+    // CTAs sharing the row chunks of one (GP, column chunk): enough to put ~2 CTAs on every SM, a power of two <= 16
+    int rs = 1;
+    while (rs < PRED_CHUNKS && (int64_t)count * ncc * rs < 2 * (int64_t)b->ctx->sm_count) rs *= 2;
+    if ((rc = ensure_dev(&sl.pq, &sl.pq_cap, (size_t)count * ncc * PRED_CHUNKS * 16)) ||
+        (rc = ensure_dev(&sl.pcount, &sl.pcount_cap, (size_t)count * ncc, true)))
+      return rc;
+    PredictArgs pa{b->Xptr, b->theta, b->alpha, b->Lm, b->DinvT, sl.pX, mstar ? sl.pms : nullptr, sl.pmu, sl.pvar,
+                   sl.pq, sl.pcount, sl.mask, xstar_stride, b->npad * b->npad, (int64_t)J * NB * NB,
+                   (int)b->n, (int)b->npad, b->d, (int)m, b->kind, gp0, rs, gpb};
+    if ((rc = launch_predict(pa, count, st))) return rc;
     b->ctx->launches++;
   } else {
-    if (!b->pmupart && (rc = dev_alloc(&b->pmupart, (size_t)B * J * PT))) return rc;
-    if (var && !b->pT && (rc = dev_alloc(&b->pT, (size_t)B * b->npad * PT))) return rc;
+    if ((rc = ensure_dev(&sl.pmupart, &sl.pmupart_cap, (size_t)count * J * PT))) return rc;
+    if (want_var && (rc = ensure_dev(&sl.pT, &sl.pT_cap, (size_t)count * b->npad * PT))) return rc;
     const int nv = (int)((b->n + KT - 1) / KT * KT);
     for (int64_t s0 = 0; s0 < m; s0 += PT) {
-      PredictTileArgs ta{b->Xtptr, b->theta, b->alpha, b->pX, mstar ? b->pms : nullptr, var ? b->pT : nullptr, b->pmupart,
-                         b->pmu, var ? b->pvar : nullptr, xstar_stride, (int)b->n, (int)b->npad, b->d, J, (int)m, b->kind,
+      PredictTileArgs ta{b->Xtptr, b->theta, b->alpha, sl.pX, mstar ? sl.pms : nullptr, want_var ? sl.pT : nullptr, sl.pmupart,
+                         sl.pmu, want_var ? sl.pvar : nullptr, xstar_stride, (int)b->n, (int)b->npad, b->d, J, (int)m, b->kind,
                          (int)s0, (int)std::min<int64_t>(PT, m - s0)};
-      if ((rc = launch_predict_cross(ta, B, st))) return rc;
+      ta.gp_off = gp0;
+      ta.mask = sl.mask;
+      ta.gpb = gpb;
+      if ((rc = launch_predict_cross(ta, count, st))) return rc;
       b->ctx->launches++;
-      if (var) {
-        // L^-1 K*: one launch per block row, B tiles of 128 x 128 each (PDMats whiten! as a blocked substitution)
+      if (want_var) {
+        // L^-1 K*: one launch per block row, `count` tiles of 128 x 128 each (PDMats whiten! as a blocked substitution)
         GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->KinvD, nullptr, b->npad * b->npad, (int64_t)J * NB * NB,
                     (int)b->npad, J, 0, GEMM_FWD_ROW, nv};
-        ga.Tm = b->pT; ga.t_stride = b->npad * PT; ga.ldt = PT;
+        ga.Tm = sl.pT; ga.t_stride = b->npad * PT; ga.ldt = PT; ga.t_gp_off = gp0;
         ga.ncols = ta.mc;
+        ga.fail = sl.mask;  // tiles of a GP without state exit at once
         // few GPs (large n, or the reference's single-GP call pattern): narrower tiles, so that a launch still fills the SMs
-        ga.colw = B >= b->ctx->sm_count ? PT : (2 * B >= b->ctx->sm_count ? PT / 2 : PT / 4);
+        ga.colw = count >= b->ctx->sm_count ? PT : (2 * count >= b->ctx->sm_count ? PT / 2 : PT / 4);
         const int ntl = (ta.mc + ga.colw - 1) / ga.colw;
         // the GPs are dealt over the stream groups: the dependent chain of J launches of one group fills the wave
-        // tails of the others (B tiles per launch are not a multiple of the SM count)
-        const int S = (B >= 8 * b->nstreams) ? b->nstreams : 1;
-        if (S > 1) GPRB_CUDA(cudaEventRecord(b->join[0], st));
+        // tails of the others (`count` tiles per launch are not a multiple of the SM count)
+        const int ns = std::min(4, b->nstreams);
+        const int S = (count >= 8 * ns) ? ns : 1;
+        if (S > 1) GPRB_CUDA(cudaEventRecord(b->join[4 * slot], st));
         for (int s = 0; s < S; ++s) {
-          const int g0 = (int)((int64_t)B * s / S), g1 = (int)((int64_t)B * (s + 1) / S);
-          cudaStream_t ss = b->stream[s];
-          if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(ss, b->join[0], 0));
-          ga.gp_off = g0;
+          const int g0 = (int)((int64_t)count * s / S), g1 = (int)((int64_t)count * (s + 1) / S);
+          cudaStream_t ss = str[s];
+          if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(ss, b->join[4 * slot], 0));
+          ga.gp_off = gp0 + g0;
           for (int i = 0; i < J; ++i) {
             ga.step = i;
             if ((rc = launch_tile_gemm(ga, ntl, g1 - g0, ss))) return rc;
             b->ctx->launches++;
           }
           if (s > 0) {
-            GPRB_CUDA(cudaEventRecord(b->join[s], ss));
-            GPRB_CUDA(cudaStreamWaitEvent(st, b->join[s], 0));
+            GPRB_CUDA(cudaEventRecord(b->join[4 * slot + s], ss));
+            GPRB_CUDA(cudaStreamWaitEvent(st, b->join[4 * slot + s], 0));
           }
         }
       }
-      if ((rc = launch_predict_finish(ta, B, st))) return rc;
+      if ((rc = launch_predict_finish(ta, count, st))) return rc;
       b->ctx->launches++;
     }
   }
-  GPRB_CUDA(cudaMemcpyAsync(mu, b->pmu, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
-  if (var) GPRB_CUDA(cudaMemcpyAsync(var, b->pvar, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
-  GPRB_CUDA(cudaStreamSynchronize(st));
+  GPRB_CUDA(cudaMemcpyAsync(sl.h_out, sl.pmu, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+  if (want_var) GPRB_CUDA(cudaMemcpyAsync(sl.h_out + nout, sl.pvar, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+  GPRB_CUDA(cudaEventRecord(sl.t1, st));
+  sl.pending = true; sl.gp0 = gp0; sl.gp1 = gp1; sl.m = m; sl.want_var = want_var;
+  return 0;
+}
+
+static int predict_collect(gprb_batch* b, int slot, double* mu, double* var) {
+  gprb_predict_slot& sl = b->ps[slot];
+  GPRB_CUDA(cudaEventSynchronize(sl.t1));
+  sl.pending = false;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, sl.t0, sl.t1) == cudaSuccess) sl.last_ms = ms;
+  const size_t nout = (size_t)(sl.gp1 - sl.gp0) * sl.m;
+  memcpy(mu, sl.h_out, sizeof(double) * nout);
+  if (var && sl.want_var) memcpy(var, sl.h_out + nout, sizeof(double) * nout);
+  return 0;
+}
+
+static int predict_check(gprb_batch* b, int slot, int gp0, int gp1, int64_t m, const double* Xstar, int64_t xstar_stride) {
+  GPRB_REQUIRE(b && Xstar, "gprb_predict: NULL argument");
+  GPRB_REQUIRE(slot == 0 || slot == 1, "gprb_predict: slot must be 0 or 1");
+  GPRB_REQUIRE(gp0 >= 0 && gp0 < gp1 && gp1 <= b->B, "gprb_predict: bad GP range");
+  GPRB_REQUIRE(m >= 1 && m <= (1 << 24), "gprb_predict: m out of range");
+  GPRB_REQUIRE(xstar_stride == 0 || xstar_stride >= m * b->d, "gprb_predict: xstar_stride must be 0 or >= d*m");
+  GPRB_REQUIRE(!b->ps[slot].pending, "gprb_predict: the slot has a prediction in flight - call gprb_predict_wait first");
+  return 0;
+}
+
+extern "C" {
+
+int gprb_predict(gprb_batch* b, int64_t m, const double* Xstar, int64_t xstar_stride, const double* mstar, double* mu,
+                 double* var) {
+  GPRB_REQUIRE(b && mu, "gprb_predict: NULL argument");
+  int rc = predict_check(b, 0, 0, b->B, m, Xstar, xstar_stride);
+  if (rc) return rc;
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  if ((rc = predict_enqueue(b, 0, 0, b->B, m, Xstar, xstar_stride, mstar, var != nullptr))) return rc;
+  return predict_collect(b, 0, mu, var);
+}
+
+int gprb_predict_async(gprb_batch* b, int32_t slot, int32_t gp0, int32_t gp1, int64_t m, const double* Xstar,
+                       int64_t xstar_stride, int32_t gps_per_block, const double* mstar, int32_t want_var) {
+  int rc = predict_check(b, slot, gp0, gp1, m, Xstar, xstar_stride);
+  if (rc) return rc;
+  GPRB_REQUIRE(gps_per_block >= 1, "gprb_predict_async: gps_per_block must be >= 1");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  return predict_enqueue(b, slot, gp0, gp1, m, Xstar, xstar_stride, mstar, want_var != 0, gps_per_block);
+}
+
+int gprb_predict_wait(gprb_batch* b, int32_t slot, double* mu, double* var) {
+  GPRB_REQUIRE(b && mu && (slot == 0 || slot == 1), "gprb_predict_wait: bad argument");
+  GPRB_REQUIRE(b->ps[slot].pending, "gprb_predict_wait: no prediction in flight on this slot");
+  GPRB_REQUIRE(!var || b->ps[slot].want_var, "gprb_predict_wait: var requested but the prediction was enqueued with want_var = 0");
+  GPRB_CUDA(cudaSetDevice(b->ctx->device));
+  return predict_collect(b, slot, mu, var);
+}
+
+int gprb_last_predict_ms(gprb_batch* b, int32_t slot, double* ms) {
+  GPRB_REQUIRE(b && ms && (slot == 0 || slot == 1), "gprb_last_predict_ms: bad argument");
+  *ms = b->ps[slot].last_ms;
   return GPRB_OK;
 }
 

@@ -16,7 +16,8 @@ constexpr int LDS_T = NB + 4;  // padded smem row (doubles): (t*132 + g) mod 16 
 constexpr int MAX_D = 62;      // 13 * bodies <= 52 in the reference (src/CState.jl:20); (MAX_D + 2) * 128 doubles fit the
                                // 64 KB landing zone the gradient kernel reuses as its reduction buffer
 constexpr int MAX_JITTER = 10; // make_posdef! retries (GaussianProcesses 0.12.4)
-constexpr int MAX_STREAMS = 8; // the GPs of one call are split over up to this many streams (GPRB200_STREAMS, default 4)
+constexpr int MAX_STREAMS = 8; // the GPs of one call are split over up to this many streams (GPRB200_STREAMS, default 4);
+                               // prediction slot s owns stream[4s .. 4s+3]
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -43,6 +44,11 @@ int eval_pass_host(gprb_batch* b, const double* theta, const uint8_t* mode, cons
 
 }  // namespace gprb
 
+struct gprb_ctx;
+namespace gprb {
+void comm_release(gprb_ctx* ctx);  // comm.cu: destroy the context's NCCL communicator and gather staging
+}
+
 struct gprb_ctx {
   int device = 0;
   int sm_count = 0;
@@ -52,6 +58,20 @@ struct gprb_ctx {
   cudaStream_t upload = nullptr;   // dataset uploads (non-blocking stream)
   cudaStream_t upload2 = nullptr;  // input transposes of a batched upload, behind upload_ev
   cudaEvent_t upload_ev = nullptr;
+  // final gather (comm.cu): NCCL communicator of this context's rank, grow-only device / pinned staging
+  void* comm = nullptr;            // ncclComm_t
+  int rank = 0, nranks = 1;
+  double* gather_dev = nullptr;    // [send | recv]
+  double* gather_host = nullptr;   // pinned, same layout
+  size_t gather_cap = 0;           // doubles
+};
+
+// One device allocation shared by the datasets of gprb_datasets_create (freed with the last member).
+struct gprb_slab {
+  double* X = nullptr;   // [count][d*n]
+  double* Xt = nullptr;  // [count][d*npad]
+  int32_t count = 0;
+  int32_t refs = 0;
 };
 
 struct gprb_dataset {
@@ -62,6 +82,27 @@ struct gprb_dataset {
   double* X = nullptr;   // device, d x n column-major (sample = contiguous column), tightly packed
   double* Xt = nullptr;  // device, Xt[p][npad]: one contiguous, zero-padded row per input dimension (TMA source)
   uint64_t version = 0;  // bumped by every upload (state reuse compares it)
+  gprb_slab* slab = nullptr;  // non-null: X / Xt point into the slab (member `slab_index`)
+  int32_t slab_index = 0;
+};
+
+// One prediction pipeline of a batch (gprb_predict_async slot): own streams, staging and scratch, so that two groups
+// of trials can be in flight at once (device predict of one group under the host projection of the other).
+struct gprb_predict_slot {
+  double* pX = nullptr; double* pms = nullptr; double* pmu = nullptr; double* pvar = nullptr;  // device
+  double* pT = nullptr; double* pmupart = nullptr; double* pq = nullptr;
+  int32_t* pcount = nullptr;   // [cap_gps] arrival counters of the split GEMV path (zero between calls)
+  int32_t* mask = nullptr;     // device [B]: 1 = GP has no evaluated state (outputs NaN)
+  size_t pX_cap = 0, pms_cap = 0, pmu_cap = 0, pvar_cap = 0, pT_cap = 0, pmupart_cap = 0, pq_cap = 0, pcount_cap = 0;
+  double* h_in = nullptr; double* h_out = nullptr;  // pinned staging: [Xstar | mstar] and [mu | var]
+  int32_t* h_mask = nullptr;                        // pinned [B]
+  size_t h_in_cap = 0, h_out_cap = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;           // device time of the last prediction
+  bool pending = false;
+  int gp0 = 0, gp1 = 0;
+  int64_t m = 0;
+  bool want_var = false;
+  double last_ms = 0.0;
 };
 
 // Per-GP device state (structure-of-arrays over the batch), all resident in HBM:
@@ -87,7 +128,8 @@ struct gprb_batch {
   double* KinvD = nullptr;        // [B][J][NB*NB] diagonal tiles of K^-1
   double* alpha = nullptr;        // [B][npad]
   double* zbuf = nullptr;         // [B][npad] forward-substitution result
-  double* jitter = nullptr;       // [B] cumulative diagonal jitter added this evaluation
+  double* jitter = nullptr;       // [B] diag_off + cumulative diagonal jitter added this evaluation
+  double* diag_off = nullptr;     // [B] fixed per-GP diagonal offset (gprb_batch_set_diag_offset), default 0
   double* logdet_part = nullptr;  // [B][J]
   int32_t* fail = nullptr;        // [B] 0 ok / first failing column+1 (LAPACK info)
   int32_t* info = nullptr;        // [B] device copy of the per-GP info
@@ -115,11 +157,8 @@ struct gprb_batch {
   std::vector<int32_t> info_last;
   std::vector<uint64_t> ds_ver;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  // prediction scratch, allocated on first use and kept (grow-only): staged test inputs / prior means / outputs,
-  // the right-hand-side block T [B][npad][PT] of the variance substitution and the per-block mean partials [B][J][PT]
-  double* pX = nullptr; double* pms = nullptr; double* pmu = nullptr; double* pvar = nullptr;
-  double* pT = nullptr; double* pmupart = nullptr;
-  size_t pX_cap = 0, pms_cap = 0, pmu_cap = 0, pvar_cap = 0;
+  // prediction pipelines (scratch allocated on first use and kept, grow-only): slot s runs on stream[4s .. 4s+3]
+  gprb_predict_slot ps[2];
   std::vector<cudaEvent_t> gemm_ev;  // profiling: start/stop pairs around every tile-GEMM launch
   int gemm_ev_used = 0;
   std::vector<double> gemm_ms;  // per tile-GEMM launch time of the last profiled evaluation, launch order

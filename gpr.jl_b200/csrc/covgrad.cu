@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_assemble(AssembleArgs g) {
 //   r2_ij = |z_i|^2 + |z_j|^2 - 2 z_i.z_j  the d-long contraction z_i.z_j runs as DMMA.8x8x4 tiles (SASS DMMA)
 // The expansion loses accuracy by ~ (d/4 + 2) eps (|z_i|^2 + |z_j|^2) in r2, i.e. half of that relative in K.
 // Parity with the reference's direct differences (1e-12 relative on K) is kept by a guard: pairs whose norm sum
-// exceeds GRAM_SMAX and whose K is not an underflow (r2 < GRAM_R2CUT) are recomputed with direct differences of the
+// exceeds GRAM_SMAX and whose K is not an underflow (r2 below the per-kernel cut-off) are recomputed with direct differences of the
 // raw inputs.  With trajectory data and sane length-scales the guard never fires (|z|^2 << 1); extreme
 // length-scales (config.json has l down to 1e-4) take the slow exact path per element.
 // One CTA (256 threads, 8 warps of 32 x 32 register tiles) = 128 rows x 64 columns of a lower tile; two CTAs per SM.
@@ -164,7 +164,14 @@ constexpr int GA_THREADS = 256;
 constexpr int GA_CW = 64;             // columns per CTA
 constexpr int GA_LDJ = GA_CW + 4;     // padded row of the column-input tile (conflict-free B fragments)
 constexpr double GRAM_SMAX = 16.0;    // (d/4 + 2) eps * 16 < 4e-14 for d <= 62
-constexpr double GRAM_R2CUT = 1500.0; // exp(-750) underflows to zero: pairs beyond it are exact zeros either way
+// Pairs whose kernel value underflows to zero are exact zeros either way and skip the exact path.  SEArd: exp(-r2/2)
+// underflows beyond r2 = 1500.  Matern: k ~ exp(-c r) with c = 1, sqrt 3, sqrt 5 only underflows beyond r = 750 / c.
+// The test is made on a LOWER bound of r2 (the expansion errs by <= (d/4 + 2) eps (|z_i|^2 + |z_j|^2) < 4e-15 ssum), so
+// near-duplicate points far from the centre (extreme length-scales, ssum ~ 1e17) are never misclassified as far apart.
+template <int KIND>
+__device__ __forceinline__ double gram_r2cut() {
+  return KIND == GPRB_KERNEL_SE_ARD ? 1500.0 : KIND == GPRB_KERNEL_MAT12_ARD ? 562500.0 : KIND == GPRB_KERNEL_MAT32_ARD ? 187500.0 : 112500.0;
+}
 
 // CTAS = resident CTAs per SM the kernel is compiled for: 3 (80 registers, a few spilled words in the prologue) whenever
 // three 71 KB input/cross-term regions fit (d <= 28: 5.7 -> 5.15 ms per 400 GPs, the phases of three CTAs interleave
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(GA_THREADS, CTAS) k_assemble_gram(AssembleArgs
     const int c = c0 + cl;
     const double ssum = nr + nj[cl];
     double r2 = fmax(ssum - 2.0 * Cs[cl * LDS_T + rl], 0.0);
-    if (ssum > GRAM_SMAX && r2 < GRAM_R2CUT && rr < n && c < n) {  // exact path: direct differences of the raw inputs
+    if (ssum > GRAM_SMAX && r2 - 4e-15 * ssum < gram_r2cut<KIND>() && rr < n && c < n) {  // exact path: direct differences of the raw inputs
       r2 = 0.0;
       for (int p = 0; p < d; ++p) {
         const double df = Xt[(int64_t)p * g.npad + rr] - Xt[(int64_t)p * g.npad + c];
@@ -557,6 +564,16 @@ __global__ void k_transpose_inputs(const double* X, double* Xt, int n, int npad,
   Xt[idx] = r < n ? X[(int64_t)r * d + p] : 0.0;
 }
 
+// all datasets of a slab in one launch: blockIdx.y = dataset
+__global__ void k_transpose_inputs_batched(const double* X, double* Xt, int n, int npad, int d) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)npad * d) return;
+  const int p = (int)(idx / npad), r = (int)(idx % npad);
+  X += (int64_t)blockIdx.y * n * d;
+  Xt += (int64_t)blockIdx.y * npad * d;
+  Xt[idx] = r < n ? X[(int64_t)r * d + p] : 0.0;
+}
+
 // make_posdef!: K_ii += 1e-6 tr(K)/n, cumulative.  For a stationary kernel tr(K)/n = s_f^2 + (s_n^2 + eps + jitter)
 // exactly, so the increment needs no pass over the matrix; the next assembly applies it.
 __global__ void k_add_jitter(const double* theta, double* jitter, const int32_t* list, int d, int count) {
@@ -660,6 +677,15 @@ int launch_transpose_inputs(const double* X, double* Xt, int n, int npad, int d,
   k_transpose_inputs<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(X, Xt, n, npad, d);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_transpose_inputs launch", __FILE__, __LINE__);
+  return 0;
+}
+
+int launch_transpose_inputs_batched(const double* X, double* Xt, int n, int npad, int d, int count, cudaStream_t stream) {
+  const int64_t total = (int64_t)npad * d;
+  dim3 grid((unsigned)((total + 255) / 256), count);
+  k_transpose_inputs_batched<<<grid, 256, 0, stream>>>(X, Xt, n, npad, d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_transpose_inputs_batched launch", __FILE__, __LINE__);
   return 0;
 }
 

@@ -302,15 +302,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
   }
 }
 
+constexpr size_t DIAG_SMEM = (size_t)(NB * LDS_T + NSB * SB * LDW + (NSB - 1) * SB * LDW) * sizeof(double);
+
+// per-device opt-in, called by gprb_init for the device of every context (see configure_tile_gemm)
+int configure_diag_factor() {
+  cudaError_t e = cudaFuncSetAttribute(k_diag_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_diag_factor)", __FILE__, __LINE__);
+  return 0;
+}
+
 int launch_diag_factor(const DiagArgs& a, int count, cudaStream_t stream) {
   if (count <= 0) return 0;
-  const size_t smem = (size_t)(NB * LDS_T + NSB * SB * LDW + (NSB - 1) * SB * LDW) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_diag_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_diag_factor)", __FILE__, __LINE__);
-    configured = true;
-  }
+  const size_t smem = DIAG_SMEM;
   k_diag_factor<<<count, DIAG_THREADS, smem, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_diag_factor launch", __FILE__, __LINE__);

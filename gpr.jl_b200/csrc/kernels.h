@@ -27,11 +27,13 @@ struct GemmArgs {
   int ncols = 128;      // valid test columns of the block (< 128: compact warp layout skips the padding columns)
   int colw = 128;       // columns per FWD_ROW tile (128, 64 or 32): tile bx owns columns bx*colw .. of the block
   int gp_off = 0;       // first GP of this launch when `list` is null (stream groups of gprb_predict)
+  int t_gp_off = 0;     // GEMM_FWD_ROW: Tm is indexed by gp - t_gp_off (the right-hand-side blocks of a GP range start at its first GP)
   const int32_t* fail = nullptr;     // [B] per-GP failure flag: tiles of a GP whose factorisation already broke down exit at once
   unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)
 };
 
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream);
+int configure_tile_gemm();    // per-device shared-memory opt-in (current device); called by gprb_init
 
 // K1: covariance assembly, lower tiles of K = K_f + (exp(2 logNoise) + eps + jitter) I ; identity in the padding.
 struct AssembleArgs {
@@ -60,6 +62,7 @@ struct DiagArgs {
   int nv;
 };
 int launch_diag_factor(const DiagArgs& a, int count, cudaStream_t stream);
+int configure_diag_factor();  // per-device shared-memory opt-in (current device); called by gprb_init
 
 // forward + backward substitution, alpha = K^-1 ymm, and mll = -1/2 (ymm'alpha + logdet + n log 2pi).
 struct SolveArgs {
@@ -97,24 +100,34 @@ int launch_grad(const GradArgs& a, int count, cudaStream_t stream);
 
 // dataset helpers
 int launch_transpose_inputs(const double* X, double* Xt, int n, int npad, int d, cudaStream_t stream);
+int launch_transpose_inputs_batched(const double* X, double* Xt, int n, int npad, int d, int count, cudaStream_t stream);
 // jitter[gp] += 1e-6 * tr(K)/n for the listed GPs (make_posdef!); applied by the next assembly
 int launch_add_jitter(const double* theta, double* jitter, const int32_t* list, int d, int count, cudaStream_t stream);
 
 // K6: posterior mean / variance
+// GPs gp_off .. gp_off + count - 1 of the batch; Xstar / mstar / mu / var / scratch are indexed by the LOCAL GP index
+// (gp - gp_off), theta / alpha / Lm / X by the global one.  mask[gp] != 0: no evaluated state, outputs NaN.
+constexpr int PRED_CHUNKS = 16;  // fixed row chunks of the split GEMV path (partials are summed in chunk order: results
+                                 // do not depend on how many CTAs share the chunks, i.e. on the batch size)
 struct PredictArgs {
   const double* const* X;  // [B] original d x n inputs
   const double* theta;
   const double* alpha;
   const double* Lm;        // V = L^-T in the strictly-upper tiles (variance only)
   const double* DinvT;     // transposed inverse diagonal blocks
-  const double* Xstar;     // d x m (+ b * xstar_stride)
-  const double* mstar;     // [B][m] or nullptr
-  double* mu;              // [B][m]
-  double* var;             // [B][m] or nullptr
+  const double* Xstar;     // d x m (+ local gp * xstar_stride)
+  const double* mstar;     // [count][m] or nullptr
+  double* mu;              // [count][m]
+  double* var;             // [count][m]
+  double* qpart;           // [count][colchunks][PRED_CHUNKS][2][8] partial mean / |L^-1 k*|^2 sums
+  int32_t* counter;        // [count * colchunks] arrival counters (zero on entry, reset by the last CTA)
+  const int32_t* mask;     // [B]
   int64_t xstar_stride, mat_stride, dinv_stride;
   int n, npad, d, m, kind;
+  int gp_off, rsplit;      // rsplit in {1, 2, 4, 8, 16}: CTAs sharing the PRED_CHUNKS row chunks of one (GP, column chunk)
+  int gpb = 1;             // consecutive GPs sharing one Xstar block (the G outputs of a trial): block = local gp / gpb
 };
-int launch_predict(const PredictArgs& a, int B, cudaStream_t stream);  // small-m path (needs V resident)
+int launch_predict(const PredictArgs& a, int count, cudaStream_t stream);  // small-m path (needs V resident)
 
 // Tiled path: cross-covariances of one chunk of <= 128 test columns -> T[B][npad][PT] (+ per-block mean partials),
 // then the forward substitution L^-1 K* runs as GEMM_FWD_ROW launches and k_predict_finish reduces.
@@ -125,15 +138,18 @@ struct PredictTileArgs {
   const double* alpha;
   const double* Xstar;      // d x m (+ b * xstar_stride)
   const double* mstar;      // [B][m] or nullptr
-  double* T;                // [B][npad][PT] or nullptr (mean only)
-  double* mupart;           // [B][J][PT]
-  double* mu;               // [B][m]
-  double* var;              // [B][m] or nullptr
+  double* T;                // [count][npad][PT] or nullptr (mean only)
+  double* mupart;           // [count][J][PT]
+  double* mu;               // [count][m]
+  double* var;              // [count][m] or nullptr
   int64_t xstar_stride;
   int n, npad, d, J, m, kind;
   int s0, mc;               // chunk: test columns s0 .. s0 + mc
+  int gp_off = 0;           // first GP of the range (local index = gp - gp_off, see PredictArgs)
+  const int32_t* mask = nullptr;  // [B] or nullptr
+  int gpb = 1;              // consecutive GPs sharing one Xstar block (see PredictArgs)
 };
-int launch_predict_cross(const PredictTileArgs& a, int B, cudaStream_t stream);
-int launch_predict_finish(const PredictTileArgs& a, int B, cudaStream_t stream);
+int launch_predict_cross(const PredictTileArgs& a, int count, cudaStream_t stream);
+int launch_predict_finish(const PredictTileArgs& a, int count, cudaStream_t stream);
 
 }  // namespace gprb

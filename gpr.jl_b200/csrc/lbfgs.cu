@@ -37,6 +37,7 @@ struct GpState {
   bool ls_prefinite = true;  // still in the "halve until finite" pre-loop
   enum Phase { NEED_DIR, IN_LS, NEED_GRAD, DONE } phase = NEED_DIR;
   bool converged = false, ls_failed = false;
+  double vclock = 0.0;  // per-GP virtual clock (opts.cost_value / cost_grad), compared with opts.time_limit
 };
 
 static double dot(const double* a, const double* b, int n) {
@@ -44,9 +45,13 @@ static double dot(const double* a, const double* b, int n) {
   for (int i = 0; i < n; ++i) s += a[i] * b[i];
   return s;
 }
+// maximum(abs, g) with Julia's semantics: NaN if any entry is NaN (fmax would drop it and report a failed gradient as 0)
 static double inf_norm(const std::vector<double>& v) {
   double m = 0;
-  for (double e : v) m = fmax(m, fabs(e));
+  for (double e : v) {
+    if (isnan(e)) return NAN;
+    m = fmax(m, fabs(e));
+  }
   return m;
 }
 
@@ -109,6 +114,7 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
     st.dx_hist.assign((size_t)m * P, 0.0); st.dg_hist.assign((size_t)m * P, 0.0); st.rho.assign(m, 0.0);
     st.fx = f[b];
     st.fg_calls = 1;
+    st.vclock = o.cost_grad;
     bool finite = isfinite(st.fx);
     for (double e : st.g) finite = finite && isfinite(e);
     if (!finite) st.phase = GpState::DONE;                                              // nothing to optimise from
@@ -165,12 +171,15 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
       fprintf(stderr, "lbfgs round: value %d grad %d retry-pending %d  %.2f ms\n", nv, ng, np,
               1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count());
     }
-    if (o.time_limit > 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > o.time_limit)
+    // wall-clock form of time_limit (whole batch); with evaluation costs set the limit is per GP on its virtual clock
+    const bool vtime = o.cost_value > 0.0 || o.cost_grad > 0.0;
+    if (!vtime && o.time_limit > 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > o.time_limit)
       timed_out = true;
     for (int b = 0; b < B; ++b) {
       GpState& st = S[b];
       if (act[b] == 1) {
         st.f_calls++;
+        st.vclock += o.cost_value;
         st.phi1 = f[b];
         // BackTracking: "halve until finite" pre-loop
         if (st.ls_prefinite && !isfinite(st.phi1) && st.iterfinite < iterfinite_max) {
@@ -204,16 +213,32 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
         st.phase = GpState::NEED_GRAD;
       } else if (act[b] == 2) {
         st.fg_calls++;
+        st.vclock += o.cost_grad;
+        const double fnew = f[b];
+        const double* gnew = &g[(size_t)b * P];
+        bool gfinite = true;
         double dxmax = 0.0;
         for (int p = 0; p < P; ++p) {
-          const double xn = theta[(size_t)b * P + p];
-          dxmax = fmax(dxmax, fabs(xn - st.x[p]));
-          st.x[p] = xn;
-          st.g[p] = g[(size_t)b * P + p];
+          gfinite = gfinite && isfinite(gnew[p]);
+          dxmax = fmax(dxmax, fabs(theta[(size_t)b * P + p] - st.x[p]));
         }
-        st.fx = f[b];
-        // assess_convergence: x/f tolerances are 0 => only exact stalls; g_abstol on the inf-norm
-        const bool x_conv = dxmax <= 0.0, f_conv = fabs(st.fx - st.f_prev) <= 0.0, g_conv = inf_norm(st.g) <= o.g_abstol;
+        // assess_convergence: x/f tolerances are 0 => only exact stalls; g_abstol on the inf-norm (NaN never converges)
+        double gmax = 0.0;
+        for (int p = 0; p < P; ++p) gmax = isnan(gnew[p]) ? NAN : fmax(gmax, fabs(gnew[p]));
+        const bool x_conv = dxmax <= 0.0, f_conv = fabs(fnew - st.f_prev) <= 0.0, g_conv = gmax <= o.g_abstol;
+        // Optim: f_increased (f_x > f_x_previous, e.g. +Inf from a re-evaluation that failed) stops the run when
+        // allow_f_increases = false (the default) and pick_best_x hands back the PREVIOUS point; a non-finite gradient
+        // ends it too ("Terminated early due to NaN in gradient").  Either way this GP keeps its last good x, f, g.
+        if (fnew > st.f_prev || !gfinite || !isfinite(fnew)) {
+          st.converged = x_conv || f_conv || g_conv;
+          st.phase = GpState::DONE;
+          continue;
+        }
+        for (int p = 0; p < P; ++p) {
+          st.x[p] = theta[(size_t)b * P + p];
+          st.g[p] = gnew[p];
+        }
+        st.fx = fnew;
         if (x_conv || f_conv || g_conv) { st.converged = true; st.phase = GpState::DONE; continue; }
         // update_h!
         double denom = 0.0;
@@ -231,10 +256,18 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
         st.phase = GpState::NEED_DIR;
         if (st.iteration >= o.iterations) st.phase = GpState::DONE;
         if (o.max_evals > 0 && st.f_calls + st.fg_calls >= o.max_evals) st.phase = GpState::DONE;
+        if (vtime && o.time_limit > 0 && st.vclock > o.time_limit) st.phase = GpState::DONE;  // this GP's own 10 s are up
       }
     }
     if (timed_out) {  // Optim checks the time limit once per iteration: GPs keep their last accepted x
-      for (int b = 0; b < B; ++b) S[b].phase = GpState::DONE;
+      for (int b = 0; b < B; ++b) {
+        GpState& st = S[b];
+        if (st.phase == GpState::NEED_GRAD) {  // the line search just accepted x + dx (f known): the step is not discarded
+          for (int p = 0; p < P; ++p) st.x[p] += st.dx[p];
+          st.fx = st.phi1;
+        }
+        st.phase = GpState::DONE;
+      }
       break;
     }
   }
@@ -269,6 +302,7 @@ void gprb_lbfgs_default_opts(gprb_lbfgs_opts* o) {
   if (!o) return;
   o->m = 10; o->iterations = 1000; o->max_evals = 0; o->ls_iterations = 1000;
   o->g_abstol = 1e-8; o->time_limit = 0.0; o->c_1 = 1e-4; o->rho_hi = 0.5; o->rho_lo = 0.1;
+  o->cost_value = 0.0; o->cost_grad = 0.0;
 }
 
 int gprb_optimize(gprb_batch* b, double* theta_inout, const gprb_lbfgs_opts* opts, gprb_opt_result* results) {

@@ -10,7 +10,6 @@
 
 namespace gprb {
 
-constexpr int PS = 8;  // test columns per CTA
 constexpr int PRED_THREADS = 256;
 
 template <int KIND>
@@ -35,19 +34,41 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
-template <int KIND>
+// Row chunk i of the split GEMV path covers rows [chunk_begin(i), chunk_begin(i + 1)): row r of L^-1 has r + 1 entries,
+// so square-root spacing gives every chunk the same share of V.  Boundaries depend on n only.
+__device__ __forceinline__ int chunk_begin(int i, int n) {
+  if (i >= PRED_CHUNKS) return n;
+  return ((int)((double)n * sqrt((double)i / (double)PRED_CHUNKS))) & ~7;
+}
+
+// grid (rsplit, ceil(m / PS), count).  The rows of one (GP, column chunk) are cut into PRED_CHUNKS fixed chunks; the
+// `rsplit` CTAs of a (GP, column chunk) take PRED_CHUNKS / rsplit consecutive chunks each, every chunk is reduced by a
+// whole CTA in a fixed order and its partial sums go to HBM; the CTA that arrives last adds the partials in chunk order.
+// So a single GP with one test column (the reference's call pattern, predictdynamics.jl:13) streams V with 16 CTAs
+// instead of one, and the result is bit-identical for every rsplit (i.e. for every batch size).
+template <int KIND, int PS>
 __global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* ks = reinterpret_cast<double*>(smem_raw);  // [PS][npad]
-  double* xs = ks + (size_t)PS * g.npad;              // [PS][d]
-  double* w = xs + PS * MAX_D;                        // [d]
+  double* xs = ks + (size_t)PS * g.npad;              // [PS][MAX_D]
+  double* w = xs + PS * MAX_D;                        // [MAX_D]
   double* red = w + MAX_D;                            // [8]
-  const int gp = blockIdx.y;
-  const int s0 = blockIdx.x * PS;
+  __shared__ int is_last;
+  const int gl = blockIdx.z, gp = g.gp_off + gl, ci = blockIdx.y, ri = blockIdx.x;
+  const int s0 = ci * PS;
   const int ns = min(PS, g.m - s0);
   const int d = g.d, n = g.n, npad = g.npad;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  if (g.mask && g.mask[gp] != 0) {  // no evaluated state: NaN, the other GPs of the call are unaffected
+    if (ri == 0 && (int)threadIdx.x < ns) {
+      const int64_t o = (int64_t)gl * g.m + s0 + threadIdx.x;
+      g.mu[o] = qnan;
+      g.var[o] = qnan;
+    }
+    return;
+  }
   const double* th = g.theta + (int64_t)gp * (d + 2);
-  const double* Xstar = g.Xstar + (int64_t)gp * g.xstar_stride;
+  const double* Xstar = g.Xstar + (int64_t)(gl / g.gpb) * g.xstar_stride;
   for (int idx = threadIdx.x; idx < PS * d; idx += PRED_THREADS) {
     const int s = idx / d, p = idx % d;
     xs[s * MAX_D + p] = s < ns ? Xstar[(int64_t)(s0 + s) * d + p] : 0.0;
@@ -57,40 +78,24 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
   const double sf2 = exp(2.0 * th[d + 1]);
   const double* X = g.X[gp];
   const double* alpha = g.alpha + (int64_t)gp * npad;
-  double mu_acc[PS];
-#pragma unroll
-  for (int s = 0; s < PS; ++s) mu_acc[s] = 0.0;
-  for (int r = threadIdx.x; r < npad; r += PRED_THREADS) {
+  const int per = PRED_CHUNKS / g.rsplit, ch0 = ri * per, ch1 = ch0 + per;
+  const int r_hi = chunk_begin(ch1, n);  // this CTA's rows only meet k*_c for c < r_hi
+  for (int r = threadIdx.x; r < r_hi; r += PRED_THREADS) {
     double r2[PS];
 #pragma unroll
     for (int s = 0; s < PS; ++s) r2[s] = 0.0;
-    if (r < n) {
-      const double* xr = X + (int64_t)r * d;
-      for (int p = 0; p < d; ++p) {
-        const double xv = xr[p], wp = w[p];
+    const double* xr = X + (int64_t)r * d;
+    for (int p = 0; p < d; ++p) {
+      const double xv = xr[p], wp = w[p];
 #pragma unroll
-        for (int s = 0; s < PS; ++s) {
-          const double df = xv - xs[s * MAX_D + p];
-          r2[s] = fma(wp, df * df, r2[s]);
-        }
+      for (int s = 0; s < PS; ++s) {
+        const double df = xv - xs[s * MAX_D + p];
+        r2[s] = fma(wp, df * df, r2[s]);
       }
     }
-    const double ar = alpha[r];
 #pragma unroll
-    for (int s = 0; s < PS; ++s) {
-      const double kv = (r < n) ? kcross<KIND>(r2[s], sf2) : 0.0;
-      ks[(size_t)s * npad + r] = kv;
-      mu_acc[s] = fma(kv, ar, mu_acc[s]);
-    }
+    for (int s = 0; s < PS; ++s) ks[(size_t)s * npad + r] = kcross<KIND>(r2[s], sf2);
   }
-  for (int s = 0; s < PS; ++s) {
-    const double tot = block_sum(mu_acc[s], red);
-    if (threadIdx.x == 0 && s < ns) {
-      const int64_t o = (int64_t)gp * g.m + s0 + s;
-      g.mu[o] = tot + (g.mstar ? g.mstar[o] : 0.0);
-    }
-  }
-  if (g.var == nullptr) return;
   __syncthreads();
   // latent variance through the factor, like the reference's whiten! (PDMats): v = L^-1 k*, var_f = s_f^2 - |v|^2.
   // L^-1 is resident as V = L^-T (strictly-upper tiles of Lm, column r of V = row r of L^-1, contiguous) plus the
@@ -98,39 +103,80 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
   const double* V = g.Lm + (int64_t)gp * g.mat_stride;
   const double* DT = g.DinvT + (int64_t)gp * g.dinv_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double q[PS];
+  const int ncc = gridDim.y;
+  double* part = g.qpart + ((int64_t)gl * ncc + ci) * (PRED_CHUNKS * 16);
+  for (int ch = ch0; ch < ch1; ++ch) {
+    const int r0 = chunk_begin(ch, n), r1 = chunk_begin(ch + 1, n);
+    double macc[PS], q[PS];
 #pragma unroll
-  for (int s = 0; s < PS; ++s) q[s] = 0.0;
-  for (int r = warp; r < n; r += PRED_THREADS / 32) {
-    const int jb = r / NB, rl = r - jb * NB;
-    double t[PS];
+    for (int s = 0; s < PS; ++s) macc[s] = q[s] = 0.0;
+    for (int r = r0 + threadIdx.x; r < r1; r += PRED_THREADS) {
+      const double ar = alpha[r];
 #pragma unroll
-    for (int s = 0; s < PS; ++s) t[s] = 0.0;
-    const double* Vr = V + (int64_t)r * npad;
-    for (int c = lane; c < jb * NB; c += 32) {
-      const double v = Vr[c];
-#pragma unroll
-      for (int s = 0; s < PS; ++s) t[s] = fma(v, ks[(size_t)s * npad + c], t[s]);
+      for (int s = 0; s < PS; ++s) macc[s] = fma(ks[(size_t)s * npad + r], ar, macc[s]);
     }
-    const double* Dr = DT + (int64_t)jb * NB * NB + (int64_t)rl * NB;  // DinvT(c, rl) = inv(L_jj)(rl, c), c <= rl
-    for (int c = lane; c <= rl; c += 32) {
-      const double v = Dr[c];
+    for (int r = r0 + warp; r < r1; r += PRED_THREADS / 32) {
+      const int jb = r / NB, rl = r - jb * NB;
+      double t[PS];
 #pragma unroll
-      for (int s = 0; s < PS; ++s) t[s] = fma(v, ks[(size_t)s * npad + jb * NB + c], t[s]);
+      for (int s = 0; s < PS; ++s) t[s] = 0.0;
+      const double* Vr = V + (int64_t)r * npad;
+      const int cend = jb * NB;
+      for (int c = lane; c < cend; c += 128) {  // four independent loads in flight per lane
+        double v[4];
+        int cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = c + 32 * u < cend;
+          cc[u] = ok ? c + 32 * u : c;
+          v[u] = ok ? Vr[cc[u]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int s = 0; s < PS; ++s) t[s] = fma(v[u], ks[(size_t)s * npad + cc[u]], t[s]);
+      }
+      const double* Dr = DT + (int64_t)jb * NB * NB + (int64_t)rl * NB;  // DinvT(c, rl) = inv(L_jj)(rl, c), c <= rl
+      for (int c = lane; c <= rl; c += 32) {
+        const double v = Dr[c];
+#pragma unroll
+        for (int s = 0; s < PS; ++s) t[s] = fma(v, ks[(size_t)s * npad + jb * NB + c], t[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < PS; ++s) {
+        double v = t[s];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        q[s] = fma(v, v, q[s]);
+      }
     }
 #pragma unroll
     for (int s = 0; s < PS; ++s) {
-      double v = t[s];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      q[s] = fma(v, v, q[s]);
+      const double mt = block_sum(macc[s], red);
+      const double qt = block_sum(lane == 0 ? q[s] : 0.0, red);
+      if (threadIdx.x == 0) { part[ch * 16 + s] = mt; part[ch * 16 + 8 + s] = qt; }
     }
   }
-  const double sn2 = exp(2.0 * th[0]);
-  for (int s = 0; s < PS; ++s) {
-    const double tot = block_sum(lane == 0 ? q[s] : 0.0, red);
-    if (threadIdx.x == 0 && s < ns) g.var[(int64_t)gp * g.m + s0 + s] = fmax(sf2 - tot, 0.0) + sn2;
+  // arrival: the last CTA of this (GP, column chunk) adds the chunk partials in chunk order
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(&g.counter[gl * ncc + ci], 1);
+    is_last = (old == g.rsplit - 1);
   }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if ((int)threadIdx.x < ns) {
+    const int s = threadIdx.x;
+    const volatile double* vp = part;
+    double mt = 0.0, qt = 0.0;
+    for (int ch = 0; ch < PRED_CHUNKS; ++ch) { mt += vp[ch * 16 + s]; qt += vp[ch * 16 + 8 + s]; }
+    const int64_t o = (int64_t)gl * g.m + s0 + s;
+    g.mu[o] = mt + (g.mstar ? g.mstar[o] : 0.0);
+    g.var[o] = fmax(sf2 - qt, 0.0) + exp(2.0 * th[0]);
+  }
+  if (threadIdx.x == 0) g.counter[gl * ncc + ci] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -151,7 +197,8 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
   double* w = xsT + d * PT;                           // [MAX_D]
   double* red = w + MAX_D;                            // [8][PT]
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 8 * PT);
-  const int gp = blockIdx.y, ib = blockIdx.x;
+  const int gl = blockIdx.y, gp = g.gp_off + gl, ib = blockIdx.x;
+  if (g.mask && g.mask[gp] != 0) return;  // no evaluated state: k_predict_finish reports NaN
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* th = g.theta + (int64_t)gp * (d + 2);
   const double* Xt = g.Xt[gp];
@@ -164,7 +211,7 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
     if (uwarp < 4 && lane == 0)
       for (int p = uwarp; p < d; p += 4) bulk_g2s(Xi + p * NB, Xt + (int64_t)p * g.npad + (int64_t)ib * NB, NB * sizeof(double), bar);
   }
-  const double* Xstar = g.Xstar + (int64_t)gp * g.xstar_stride + (int64_t)g.s0 * d;
+  const double* Xstar = g.Xstar + (int64_t)(gl / g.gpb) * g.xstar_stride + (int64_t)g.s0 * d;
   for (int idx = threadIdx.x; idx < d * PT; idx += PC_THREADS) {
     const int s = idx / d, p = idx - s * d;  // consecutive threads walk one test column: coalesced global reads
     xsT[p * PT + s] = s < g.mc ? Xstar[(int64_t)s * d + p] : 0.0;
@@ -195,7 +242,7 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
     for (int q = 0; q < 4; ++q) {
       const int s = lane + 32 * q;
       const double kv = (r < g.n && s < g.mc) ? kcross<KIND>(r2[q], sf2) : 0.0;
-      if (g.T) g.T[((int64_t)gp * g.npad + r) * PT + s] = kv;
+      if (g.T) g.T[((int64_t)gl * g.npad + r) * PT + s] = kv;
       macc[q] = fma(kv, ar, macc[q]);
     }
   }
@@ -206,7 +253,7 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
     double sum = 0.0;
 #pragma unroll
     for (int k = 0; k < PC_THREADS / 32; ++k) sum += red[k * PT + threadIdx.x];
-    g.mupart[((int64_t)gp * g.J + ib) * PT + threadIdx.x] = sum;
+    g.mupart[((int64_t)gl * g.J + ib) * PT + threadIdx.x] = sum;
   }
 }
 
@@ -214,11 +261,19 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
 // var = max(s_f^2 - sum_r T(r,s)^2, 0) + exp(2 logNoise), fixed summation order.
 __global__ void __launch_bounds__(512) k_predict_finish(PredictTileArgs g) {
   __shared__ double red[4][PT];
-  const int gp = blockIdx.x, s = threadIdx.x & (PT - 1), part = threadIdx.x >> 7;
+  const int gl = blockIdx.x, gp = g.gp_off + gl, s = threadIdx.x & (PT - 1), part = threadIdx.x >> 7;
   const int d = g.d;
   const double* th = g.theta + (int64_t)gp * (d + 2);
+  if (g.mask && g.mask[gp] != 0) {  // no evaluated state: NaN rows, the other GPs of the call are unaffected
+    if (part == 0 && s < g.mc) {
+      const int64_t o = (int64_t)gl * g.m + g.s0 + s;
+      g.mu[o] = __longlong_as_double(0x7ff8000000000000LL);
+      if (g.var) g.var[o] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    return;
+  }
   if (g.var) {
-    const double* T = g.T + (int64_t)gp * g.npad * PT + s;
+    const double* T = g.T + (int64_t)gl * g.npad * PT + s;
     const int per = (g.n + 3) / 4, r0 = part * per, r1 = min(g.n, r0 + per);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int r = r0;
@@ -231,9 +286,9 @@ __global__ void __launch_bounds__(512) k_predict_finish(PredictTileArgs g) {
   }
   __syncthreads();
   if (part != 0 || s >= g.mc) return;
-  const int64_t o = (int64_t)gp * g.m + g.s0 + s;
+  const int64_t o = (int64_t)gl * g.m + g.s0 + s;
   double mu = 0.0;
-  for (int ib = 0; ib < g.J; ++ib) mu += g.mupart[((int64_t)gp * g.J + ib) * PT + s];
+  for (int ib = 0; ib < g.J; ++ib) mu += g.mupart[((int64_t)gl * g.J + ib) * PT + s];
   g.mu[o] = mu + (g.mstar ? g.mstar[o] : 0.0);
   if (g.var) {
     const double q = (red[0][s] + red[1][s]) + (red[2][s] + red[3][s]);
@@ -241,7 +296,8 @@ __global__ void __launch_bounds__(512) k_predict_finish(PredictTileArgs g) {
   }
 }
 
-int launch_predict_cross(const PredictTileArgs& a, int B, cudaStream_t stream) {
+int launch_predict_cross(const PredictTileArgs& a, int count, cudaStream_t stream) {
+  const int B = count;
   if (B <= 0 || a.mc <= 0) return 0;
   const size_t smem = ((size_t)a.d * NB + (size_t)a.d * PT + MAX_D + 8 * PT) * sizeof(double) + 16;
   dim3 grid(a.J, B);
@@ -262,7 +318,8 @@ int launch_predict_cross(const PredictTileArgs& a, int B, cudaStream_t stream) {
   return 0;
 }
 
-int launch_predict_finish(const PredictTileArgs& a, int B, cudaStream_t stream) {
+int launch_predict_finish(const PredictTileArgs& a, int count, cudaStream_t stream) {
+  const int B = count;
   if (B <= 0 || a.mc <= 0) return 0;
   k_predict_finish<<<B, 512, 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
@@ -270,19 +327,25 @@ int launch_predict_finish(const PredictTileArgs& a, int B, cudaStream_t stream) 
   return 0;
 }
 
-int launch_predict(const PredictArgs& a, int B, cudaStream_t stream) {
-  if (B <= 0 || a.m <= 0) return 0;
-  const size_t smem = ((size_t)PS * a.npad + PS * MAX_D + MAX_D + 8) * sizeof(double);
+int launch_predict(const PredictArgs& a, int count, cudaStream_t stream) {
+  if (count <= 0 || a.m <= 0) return 0;
+  const int ps = a.m <= 1 ? 1 : a.m <= 2 ? 2 : a.m <= 4 ? 4 : 8;  // test columns per CTA (smem: ps * npad doubles)
+  const size_t smem = ((size_t)ps * a.npad + ps * MAX_D + MAX_D + 8) * sizeof(double);
   if (smem > 227 * 1024) {
-    set_error("gprb_predict: n too large for the shared-memory cross-covariance block (npad <= 3500)");
+    set_error("gprb_predict: n too large for the shared-memory cross-covariance block");
     return GPRB_ERR_ARG;
   }
-  dim3 grid((a.m + PS - 1) / PS, B);
+  dim3 grid(a.rsplit, (a.m + ps - 1) / ps, count);
   cudaError_t e;
-#define GPRB_PRED_CASE(K)                                                                                   \
-  e = cudaFuncSetAttribute(k_predict<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_predict)", __FILE__, __LINE__);         \
-  k_predict<K><<<grid, PRED_THREADS, smem, stream>>>(a);
+#define GPRB_PRED_LAUNCH(K, P)                                                                                 \
+  e = cudaFuncSetAttribute(k_predict<K, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_predict)", __FILE__, __LINE__);            \
+  k_predict<K, P><<<grid, PRED_THREADS, smem, stream>>>(a);
+#define GPRB_PRED_CASE(K)                                   \
+  if (ps == 1) { GPRB_PRED_LAUNCH(K, 1) }                   \
+  else if (ps == 2) { GPRB_PRED_LAUNCH(K, 2) }              \
+  else if (ps == 4) { GPRB_PRED_LAUNCH(K, 4) }              \
+  else { GPRB_PRED_LAUNCH(K, 8) }
   switch (a.kind) {
     case GPRB_KERNEL_SE_ARD: GPRB_PRED_CASE(0) break;
     case GPRB_KERNEL_MAT12_ARD: GPRB_PRED_CASE(1) break;
@@ -290,6 +353,7 @@ int launch_predict(const PredictArgs& a, int B, cudaStream_t stream) {
     default: GPRB_PRED_CASE(3) break;
   }
 #undef GPRB_PRED_CASE
+#undef GPRB_PRED_LAUNCH
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_predict launch", __FILE__, __LINE__);
   return 0;

@@ -189,7 +189,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   const int64_t grow = (int64_t)tc.i * NB, gcol = (int64_t)tc.j * (fwd ? g.colw : NB);
   double acc[8][4][2];
   if (fwd) {
-    const double* Tin = g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt;
+    const double* Tin = g.Tm + (int64_t)(gp - g.t_gp_off) * g.t_stride + gcol + grow * g.ldt;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -363,7 +363,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
         Cout[grow + r + (gcol + cc + 1) * npad] = -acc[mi][ni][1];
       }
   } else {  // W(i,j) = -acc, stored transposed as V(j,i); FWD_ROW (parked operand sum - T(i,:)): row r of the solved block
-    double* outp = fwd ? g.Tm + (int64_t)gp * g.t_stride + gcol + grow * g.ldt : Cout + gcol + grow * npad;
+    double* outp = fwd ? g.Tm + (int64_t)(gp - g.t_gp_off) * g.t_stride + gcol + grow * g.ldt : Cout + gcol + grow * npad;
     const int64_t ldo = fwd ? g.ldt : npad;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
       if (kb == tc.a_diag_kb) { srcA = DinvT + (int64_t)kb * NB * NB; ldA = NB; }
       else { srcA = Lm + (int64_t)tc.i * NB + (int64_t)kb * NB * npad; ldA = npad; }
       if (kb == tc.b_diag_kb) { srcB = DinvT + (int64_t)kb * NB * NB; ldB = NB; }
-      else if (g.mode == GEMM_FWD_ROW) { srcB = g.Tm + (int64_t)gp * g.t_stride + (int64_t)tc.j * g.colw + (int64_t)kb * NB * g.ldt; ldB = g.ldt; }
+      else if (g.mode == GEMM_FWD_ROW) { srcB = g.Tm + (int64_t)(gp - g.t_gp_off) * g.t_stride + (int64_t)tc.j * g.colw + (int64_t)kb * NB * g.ldt; ldB = g.ldt; }
       else { srcB = Lm + (int64_t)tc.j * NB + (int64_t)kb * NB * npad; ldB = npad; }
       const int cend = (kb == g.J - 1) ? last_kb_chunks : NB / KT;
       for (int c = 0; c < cend; ++c) {
@@ -469,14 +469,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tile_gemm(GemmArgs g) {
   else consume_tile<true>(g, tc, stages, rbuf, full, empty, rfull, rempty, gp, nchunks, rows_valid);
 }
 
+// The dynamic shared-memory opt-in is a per-device function attribute: gprb_init calls this for the device of every
+// context it creates (a process-wide "configured" flag would leave a second GPU of the same process un-opted-in).
+int configure_tile_gemm() {
+  cudaError_t e = cudaFuncSetAttribute(k_tile_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_tile_gemm)", __FILE__, __LINE__);
+  return 0;
+}
+
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream) {
   if (ntiles <= 0 || count <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tile_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_tile_gemm)", __FILE__, __LINE__);
-    configured = true;
-  }
   dim3 grid(ntiles, count);
   k_tile_gemm<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(g);
   cudaError_t e = cudaGetLastError();

@@ -33,7 +33,7 @@ CONFIGS = {
     "FB": dict(system="FB", n=2000, trials=100, theta_key=None, config_id=4),
 }
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _body_state(phi, psi, offset):
@@ -100,7 +100,7 @@ def make_trial(system: str, n: int, seed: int, noise: float = 1e-3, n_test: int 
 
 
 def load_theta_table():
-    with open(os.path.join(_GOLDEN, "theta0_config.json")) as f:
+    with open(os.path.join(_HERE, "theta0_config.json")) as f:
         return json.load(f)
 
 
@@ -109,7 +109,7 @@ def theta0(system: str, X: np.ndarray, key: str | None = None, log_noise: float 
 
     With ``key`` the values come from the reference's examples/config/config.json entry of that name
     (``[s_f, l_1..l_d]`` natural units -> ``SEArd(log.(l), log(s_f))``, CPnoise.jl:38); the handful of keys the
-    configs use are committed in tests/golden/theta0_config.json.  Otherwise the rule of
+    configs use are committed next to this file (theta0_config.json, extracted by tests/golden/make_theta0_config.py).  Otherwise the rule of
     examples/maximal_coordinates/FBparam.jl:23-26 without its random factor: s_f = 1, l_d = 10 / std_d (std 0 -> 1000)."""
     d = X.shape[0]
     if key is not None:

@@ -5,7 +5,8 @@ Per trial the reference does, sequentially on one CPU thread:
     for each output k:  kernel = SEArd(log.(params[2:end]), log(params[1])); gp = GP(X, y_k, mean, kernel); optimize!(gp, ...)
     for each test state: predictdynamics(mechanism, gps, x0, steps, getvomega)      (examples/utils/predictdynamics.jl:7-22)
 Here all G x T GPs of the trials resident on this GPU are built into ONE GPBatch, optimised in lock-step with one
-library call, and every rollout step predicts all (trial, test state, GP) means in one call.  The physics between
+library call, and every rollout step predicts all (trial, test state, GP) means of a trial group in one call, two
+groups alternating so that the device predicts one while the host projects the other.  The physics between
 two steps - ``getvomega`` -> ``projectv!`` -> ``updatestate!`` - stays a host callback (ConstrainedDynamics.jl is not
 part of this path).
 """
@@ -42,20 +43,56 @@ def fit_trials(trials, params, mean_factory=None, method=None, options=None):
     return batch, res
 
 
-def predictdynamics(batch, trials_G, start_states, steps, step_fn, var=False):
+def predictdynamics(batch, trials_G, start_states, steps, step_fn, var=False, overlap=True, timing=None):
     """Batched ``predictdynamics`` (examples/utils/predictdynamics.jl:7-22).
 
     batch        GPBatch holding the GPs of T trials, trial-major (G consecutive GPs per trial)
     trials_G     G (GPs per trial)
     start_states list over trials of (d, m) arrays - the m test states of each trial
     step_fn(trial, states (d,m), mu (G,m)) -> next states (d,m): host callback doing getvomega + projectv! + updatestate!
-    Returns the list of final (d, m) state blocks.  One gprb_predict call per rollout step for all trials/states/GPs."""
+                 (src/projections/implicitProjection.jl:80-107 stays on the host)
+    Returns the list of final (d, m) state blocks.
+
+    overlap=True (default, T >= 2): the trials are cut into two groups that alternate on the two prediction pipelines
+    of the library (gprb_predict_async / gprb_predict_wait): while the host projects the states of one group, the device
+    predicts the other - the per-step chain  H2D states -> predict -> D2H mu -> host projectv!  of predictdynamics.jl:11-19
+    is hidden behind the other group's host work instead of serialising with it.  The G GPs of a trial share one
+    uploaded state block.  overlap=False: one synchronous gprb_predict per step for all trials (same results, bit for bit).
+    timing: optional dict that receives host_s (time inside step_fn), wait_s (host blocked on the device), total_s."""
+    import time
     T = len(start_states)
-    assert batch.B == T * trials_G
+    G = trials_G
+    assert batch.B == T * G
     states = [np.asfortranarray(np.asarray(s, dtype=np.float64)) for s in start_states]
-    for _ in range(steps):
-        blocks = [states[b // trials_G] for b in range(batch.B)]
-        mu, _ = batch.predict_y(blocks, var=var, per_gp=True)
-        for t in range(T):
-            states[t] = np.asfortranarray(step_fn(t, states[t], mu[t * trials_G:(t + 1) * trials_G]))
+    t_host = t_wait = 0.0
+    t_start = time.perf_counter()
+    if not overlap or T < 2:
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            batch.predict_async(0, 0, batch.B, states, var=var, gps_per_block=G)
+            mu, _ = batch.predict_wait(0)
+            t1 = time.perf_counter()
+            for t in range(T):
+                states[t] = np.asfortranarray(step_fn(t, states[t], mu[t * G:(t + 1) * G]))
+            t_wait += t1 - t0
+            t_host += time.perf_counter() - t1
+    else:
+        cut = (0, T // 2, T)  # group g = trials cut[g] .. cut[g+1]-1 on pipeline slot g
+        for g in (0, 1):
+            batch.predict_async(g, cut[g] * G, cut[g + 1] * G, states[cut[g]:cut[g + 1]], var=var, gps_per_block=G)
+        for step in range(steps):
+            for g in (0, 1):
+                t0 = time.perf_counter()
+                mu, _ = batch.predict_wait(g)
+                t1 = time.perf_counter()
+                for t in range(cut[g], cut[g + 1]):
+                    k = t - cut[g]
+                    states[t] = np.asfortranarray(step_fn(t, states[t], mu[k * G:(k + 1) * G]))
+                t2 = time.perf_counter()
+                if step + 1 < steps:  # next step of this group goes to the device while the host turns to the other group
+                    batch.predict_async(g, cut[g] * G, cut[g + 1] * G, states[cut[g]:cut[g + 1]], var=var, gps_per_block=G)
+                t_wait += t1 - t0
+                t_host += t2 - t1
+    if timing is not None:
+        timing.update(host_s=t_host, wait_s=t_wait, total_s=time.perf_counter() - t_start)
     return states

@@ -170,12 +170,17 @@ class LBFGS:
 
 @dataclass
 class Options:
-    """Optim.Options subset.  ``time_limit`` is wall-clock (the reference passes 10 s per GP, CPnoise.jl:41) and
-    applies to the whole batch here; ``max_evals`` is the deterministic stopping rule used for parity."""
+    """Optim.Options subset.  The reference gives every GP its own ``time_limit=10.`` seconds of CPU wall clock
+    (CPnoise.jl:41).  With ``cost_value`` / ``cost_grad`` (seconds one value-only / value+gradient evaluation takes on the
+    machine being emulated, e.g. the reference CPU) the limit runs on a deterministic PER-GP virtual clock - what
+    "10 s per GP" means there, reproducibly; without them ``time_limit`` is the wall clock of the whole lock-step
+    batch.  ``max_evals`` (per-GP cap on evaluations) and ``iterations`` are the other deterministic stopping rules."""
     time_limit: float = float("nan")
     iterations: int = 1000
     g_abstol: float = 1e-8
     max_evals: int = 0
+    cost_value: float = 0.0
+    cost_grad: float = 0.0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,6 +212,39 @@ class _Context:
         out = (C.c_int64 * 4)()
         self.lib.check(self.lib.dll.gprb_device_info(self.handle, out))
         return {"sm_count": out[0], "clock_khz": out[1], "l2_bytes": out[2], "free_bytes": out[3]}
+
+    # -- multi-GPU: the library's own NCCL communicator (one rank per process) and the final gather ----------
+    def comm_init(self, rank=None, world=None):
+        """Join this process's context into the library's NCCL clique.  Rank 0 draws the unique id
+        (gprb_comm_unique_id) and it travels through torch.distributed's broadcast - any host-side channel would do
+        (Distributed.jl / MPI / a file on the Julia side); the data path itself never touches torch."""
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+        if world == 1 or getattr(self, "_comm", False):
+            return
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self.lib.check(self.lib.dll.gprb_comm_unique_id(buf))
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda(self.device)
+        dist.broadcast(t, 0)
+        idb = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.lib.check(self.lib.dll.gprb_comm_init_rank(self.handle, world, rank, idb))
+        self._comm = True
+
+    def gather(self, local: dict, n_rows: int, width: int):
+        """gprb_gather: {global row id -> (width,) float64} of this rank -> (n_rows, width) on every rank (NaN rows
+        where nobody contributed).  One ncclAllGather over NVLink inside libgprb200.so."""
+        ids = np.ascontiguousarray(sorted(local), dtype=np.int32)
+        rows = np.ascontiguousarray(np.stack([np.asarray(local[int(i)], dtype=np.float64) for i in ids])
+                                    if len(ids) else np.zeros((0, width)))
+        out = np.empty((n_rows, width))
+        self.lib.check(self.lib.dll.gprb_gather(self.handle, n_rows, width, len(ids),
+                                                ids.ctypes.data_as(C.POINTER(C.c_int32)), _d(rows), _d(out)))
+        return out
 
 
 def context():
@@ -300,7 +338,6 @@ class GPBatch:
                 raise ValueError("all GPs of a batch must share d, n and the kernel family")
         self.d, self.n, self.P, self.B = d, n, d + 2, len(gps)
         self._ds = {}
-        self._keep = []
         ds_handles = (C.c_void_p * self.B)()
         ymm = np.empty((self.B, n))
         # per-GP results of the last evaluation (GPE.mll / .dmll / .info read them); seeded with what the GPs carry
@@ -312,15 +349,22 @@ class GPBatch:
         for b, r in enumerate(prev):
             if r[1] is not None:
                 self._grad[b], self._has_grad[b] = r[1], True
+        # all distinct training sets of the batch live in ONE device allocation and go up in one copy + one transpose
+        # launch (gprb_datasets_create); the host block is (T, n, d) C-order == T column-major d x n matrices back to back
+        uniq = {}
+        for g in gps:
+            uniq.setdefault(id(g.x), g.x)
+        self._keep = list(uniq.values())
+        block = np.empty((len(uniq), n, d))
+        for t, Xu in enumerate(self._keep):
+            block[t] = Xu.T
+        hs = (C.c_void_p * len(uniq))()
+        ptrs = (C.POINTER(C.c_double) * len(uniq))(*[_d(block[t]) for t in range(len(uniq))])
+        self.lib.check(self.lib.dll.gprb_datasets_create(self.ctx.handle, len(uniq), n, d, ptrs, d, hs))
+        for key, h in zip(uniq, hs):
+            self._ds[key] = C.c_void_p(h)
         for b, g in enumerate(gps):
-            key = id(g.x)
-            if key not in self._ds:
-                Xc = as_f64(g.x.T)  # (n, d) C-order == d x n column-major
-                h = C.c_void_p()
-                self.lib.check(self.lib.dll.gprb_dataset_create(self.ctx.handle, n, d, _d(Xc), d, C.byref(h)))
-                self._ds[key] = h
-                self._keep.append(g.x)
-            ds_handles[b] = self._ds[key]
+            ds_handles[b] = self._ds[id(g.x)]
             g._batch, g._slot = self, b
         # m(X) is theta-independent (zero-parameter means, src/mDynamics.jl:29-31): evaluated once per training set,
         # column-major across the GPs of a trial so a shared MDCache hits for the other G-1 outputs.
@@ -438,6 +482,11 @@ class GPBatch:
             self.lib.check(self.lib.dll.gprb_batch_set_targets(self.handle, _d(ymm)))
             self.ymm = ymm
 
+    def set_diag_offset(self, offset=None):
+        """gprb_batch_set_diag_offset: fixed per-GP nugget added to the diagonal of K (None resets it)."""
+        off = None if offset is None else as_f64(np.broadcast_to(np.asarray(offset, dtype=np.float64), (self.B,)).copy())
+        self.lib.check(self.lib.dll.gprb_batch_set_diag_offset(self.handle, _d(off)))
+
     def update_mll(self):
         return self.eval(grad=False)
 
@@ -458,6 +507,7 @@ class GPBatch:
         o.ls_iterations = method.linesearch.iterations
         o.g_abstol = options.g_abstol
         o.time_limit = options.time_limit if math.isfinite(options.time_limit) else 0.0
+        o.cost_value, o.cost_grad = options.cost_value, options.cost_grad
         o.c_1, o.rho_hi, o.rho_lo = method.linesearch.c_1, method.linesearch.rho_hi, method.linesearch.rho_lo
         theta = as_f64(self.get_params()).copy()
         res = (OptResult * self.B)()
@@ -496,6 +546,50 @@ class GPBatch:
         v = np.empty((self.B, m)) if var else None
         self.lib.check(self.lib.dll.gprb_predict(self.handle, m, _d(Xs), stride, _d(mstar), _d(mu), _d(v)))
         return mu, v
+
+    def predict_async(self, slot, gp0, gp1, blocks, var=False, gps_per_block=1):
+        """gprb_predict_async: enqueue the prediction of GPs gp0..gp1-1 on pipeline ``slot`` (0 or 1) and return at
+        once.  ``blocks``: one d x m array shared by the range, or a sequence of d x m blocks, one per ``gps_per_block``
+        consecutive GPs (the G outputs of a trial read the trial's own states).  Prior means m(x*) are evaluated here
+        on the host (src/mDynamics.jl:41-55) before the call, like predict_y."""
+        cnt = gp1 - gp0
+        if isinstance(blocks, np.ndarray) and blocks.ndim == 2:
+            Xs, stride, m = as_f64(blocks.T), 0, blocks.shape[1]
+            cols = [blocks] * cnt
+        else:
+            blks = [np.asarray(x, dtype=np.float64) for x in blocks]
+            if len(blks) != (cnt + gps_per_block - 1) // gps_per_block:
+                raise ValueError("one test block per gps_per_block GPs expected")
+            m = blks[0].shape[1]
+            Xs = np.ascontiguousarray(np.stack([c.T for c in blks]))  # (blocks, m, d)
+            stride = m * self.d
+            cols = [blks[k // gps_per_block] for k in range(cnt)]
+        mstar = None
+        if not all(isinstance(g.mean, MeanZero) for g in self.gps[gp0:gp1]):
+            mstar = np.ascontiguousarray(np.stack(self._means_range(gp0, gp1, cols)))
+        self.lib.check(self.lib.dll.gprb_predict_async(self.handle, slot, gp0, gp1, m, _d(Xs), stride, gps_per_block,
+                                                       _d(mstar), 1 if var else 0))
+        self._pending = getattr(self, "_pending", {})
+        self._pending[slot] = (cnt, m, var)
+
+    def predict_wait(self, slot):
+        """gprb_predict_wait -> (mu (cnt, m), var (cnt, m) | None) of the prediction enqueued on ``slot``."""
+        cnt, m, var = self._pending.pop(slot)
+        mu = np.empty((cnt, m))
+        v = np.empty((cnt, m)) if var else None
+        self.lib.check(self.lib.dll.gprb_predict_wait(self.handle, slot, _d(mu), _d(v)))
+        return mu, v
+
+    def last_predict_ms(self, slot=0):
+        out = np.zeros(1)
+        self.lib.check(self.lib.dll.gprb_last_predict_ms(self.handle, slot, _d(out)))
+        return float(out[0])
+
+    def _means_range(self, gp0, gp1, cols):
+        """m(x*) for the GPs gp0..gp1-1 (cols[k] = d x m block of GP gp0+k), MDCache order preserved."""
+        sub = GPBatch.__new__(GPBatch)
+        sub.gps, sub.B = self.gps[gp0:gp1], gp1 - gp0
+        return GPBatch._means(sub, cols)
 
     # -- parity taps --------------------------------------------------------------------------
     def _tap(self, fn, b, shape):

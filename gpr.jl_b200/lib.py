@@ -10,11 +10,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 EXPORTS = [
-    "gprb_version", "gprb_last_error", "gprb_init", "gprb_destroy", "gprb_device_info",
-    "gprb_dataset_create", "gprb_dataset_update", "gprb_datasets_update", "gprb_dataset_destroy",
-    "gprb_batch_create", "gprb_batch_set_targets", "gprb_batch_destroy",
-    "gprb_eval", "gprb_eval_mixed", "gprb_eval_device", "gprb_lbfgs_default_opts", "gprb_optimize", "gprb_lbfgs_selftest", "gprb_predict",
+    "gprb_version", "gprb_last_error", "gprb_init", "gprb_init_multi", "gprb_destroy", "gprb_device_info",
+    "gprb_dataset_create", "gprb_datasets_create", "gprb_dataset_update", "gprb_datasets_update", "gprb_dataset_destroy",
+    "gprb_batch_create", "gprb_batch_set_targets", "gprb_batch_set_diag_offset", "gprb_batch_destroy",
+    "gprb_eval", "gprb_eval_mixed", "gprb_eval_device", "gprb_lbfgs_default_opts", "gprb_optimize", "gprb_lbfgs_selftest",
+    "gprb_predict", "gprb_predict_async", "gprb_predict_wait", "gprb_last_predict_ms",
     "gprb_get_K", "gprb_get_chol", "gprb_get_alpha", "gprb_get_Kinv",
+    "gprb_comm_unique_id", "gprb_comm_init_rank", "gprb_gather", "gprb_gather_multi",
     "gprb_set_profiling", "gprb_last_stage_ms", "gprb_last_gemm_launch_ms", "gprb_launch_count",
 ]
 
@@ -28,7 +30,8 @@ class GprbError(RuntimeError):
 class LbfgsOpts(C.Structure):
     _fields_ = [("m", C.c_int32), ("iterations", C.c_int32), ("max_evals", C.c_int32), ("ls_iterations", C.c_int32),
                 ("g_abstol", C.c_double), ("time_limit", C.c_double),
-                ("c_1", C.c_double), ("rho_hi", C.c_double), ("rho_lo", C.c_double)]
+                ("c_1", C.c_double), ("rho_hi", C.c_double), ("rho_lo", C.c_double),
+                ("cost_value", C.c_double), ("cost_grad", C.c_double)]
 
 
 class OptResult(C.Structure):
@@ -62,14 +65,17 @@ class Library:
         L.gprb_version.restype = C.c_int
         L.gprb_last_error.restype = C.c_char_p
         L.gprb_init.argtypes = [C.POINTER(_vp), C.c_int]
+        L.gprb_init_multi.argtypes = [C.POINTER(_vp), C.c_int32, C.POINTER(C.c_int)]
         L.gprb_destroy.argtypes = [_vp]
         L.gprb_device_info.argtypes = [_vp, C.POINTER(C.c_int64)]
         L.gprb_dataset_create.argtypes = [_vp, C.c_int64, C.c_int32, _dp, C.c_int64, C.POINTER(_vp)]
+        L.gprb_datasets_create.argtypes = [_vp, C.c_int32, C.c_int64, C.c_int32, C.POINTER(_dp), C.c_int64, C.POINTER(_vp)]
         L.gprb_dataset_update.argtypes = [_vp, _dp, C.c_int64]
         L.gprb_datasets_update.argtypes = [_vp, C.c_int32, C.POINTER(_vp), C.POINTER(_dp), C.c_int64]
         L.gprb_dataset_destroy.argtypes = [_vp]
         L.gprb_batch_create.argtypes = [_vp, C.c_int32, C.POINTER(_vp), _dp, C.c_int32, C.POINTER(_vp)]
         L.gprb_batch_set_targets.argtypes = [_vp, _dp]
+        L.gprb_batch_set_diag_offset.argtypes = [_vp, _dp]
         L.gprb_batch_destroy.argtypes = [_vp]
         L.gprb_eval.argtypes = [_vp, _dp, C.POINTER(C.c_uint8), _dp, _dp, C.POINTER(C.c_int32)]
         L.gprb_eval_mixed.argtypes = [_vp, _dp, C.POINTER(C.c_uint8), _dp, _dp, C.POINTER(C.c_int32)]
@@ -79,6 +85,14 @@ class Library:
         L.gprb_optimize.argtypes = [_vp, _dp, C.POINTER(LbfgsOpts), C.POINTER(OptResult)]
         L.gprb_lbfgs_selftest.argtypes = [C.c_int32, C.c_int32, _dp, C.POINTER(LbfgsOpts), C.c_double, C.POINTER(OptResult)]
         L.gprb_predict.argtypes = [_vp, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp]
+        L.gprb_predict_async.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _dp, C.c_int64, C.c_int32, _dp, C.c_int32]
+        L.gprb_predict_wait.argtypes = [_vp, C.c_int32, _dp, _dp]
+        L.gprb_last_predict_ms.argtypes = [_vp, C.c_int32, _dp]
+        L.gprb_comm_unique_id.argtypes = [C.c_void_p]
+        L.gprb_comm_init_rank.argtypes = [_vp, C.c_int32, C.c_int32, C.c_void_p]
+        _ip = C.POINTER(C.c_int32)
+        L.gprb_gather.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _ip, _dp, _dp]
+        L.gprb_gather_multi.argtypes = [C.POINTER(_vp), C.c_int32, C.c_int32, C.c_int32, _ip, C.POINTER(_ip), C.POINTER(_dp), _dp]
         for f in ("gprb_get_K", "gprb_get_chol", "gprb_get_alpha", "gprb_get_Kinv"):
             getattr(L, f).argtypes = [_vp, C.c_int32, _dp]
         L.gprb_set_profiling.argtypes = [_vp, C.c_int32]

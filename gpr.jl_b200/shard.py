@@ -5,7 +5,11 @@ The reference's only data-parallel axis is the trial index: ``Threads.@threads f
 (examples/maximal_coordinates/CPnoise.jl:13-17).  Here one process drives one GPU (torchrun), trial t lives on rank
 ``t mod world`` with all G GPs of the trial co-located (they share X), nothing is exchanged while optimising or
 predicting, and one all-gather of the small per-trial results (theta*, mll, info, predictions) replaces the
-lock-guarded result callbacks of core.jl:47-56.  Works on NCCL (GPU tensors) and gloo (CPU tensors, tests).
+lock-guarded result callbacks of core.jl:47-56.
+
+On GPUs the gather is ``gprb_gather`` - one ``ncclAllGather`` inside libgprb200.so on the library's own communicator
+(``gp.context().comm_init()``), the entry point a Julia host binds as well.  The torch.distributed form below is the
+host-logic twin used by the world_size-2 gloo tests on CPU (same padding / scatter-by-trial-id scheme).
 """
 from __future__ import annotations
 
@@ -21,12 +25,15 @@ def owner_of(trial: int, world: int) -> int:
     return trial % world
 
 
-def gather_trial_results(local: dict, n_trials: int, width: int, device=None):
-    """All-gather per-trial result rows.
+def gather_trial_results(local: dict, n_trials: int, width: int, device=None, ctx=None):
+    """All-gather per-trial result rows.  ``ctx``: a gp.context() whose comm_init() ran -> gprb_gather (NCCL inside
+    the library); otherwise torch.distributed (gloo on CPU).
 
     local: {trial index -> 1-D float64 array of length ``width``} for the trials this rank owns.
     Returns an (n_trials, width) array on every rank, rows in trial order.  Equal-count padding keeps it a single
     fixed-size collective (latency-bound: <= ~50 KB per trial)."""
+    if ctx is not None and getattr(ctx, "_comm", False):
+        return ctx.gather(local, n_trials, width)
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

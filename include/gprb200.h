@@ -27,7 +27,11 @@
  *         -1       not positive definite after 10 jitters  => mll = -Inf (shim maps to objective +Inf)
  *         -2       non-finite theta / kernel matrix        => mll = -Inf
  *   - Caller owns every host buffer; handles own device memory.  Calls are synchronous on return.
- *   - One gprb_ctx per process and GPU (one process per GPU; ranks are launched by torchrun / Distributed.jl).
+ *   - One gprb_ctx per GPU.  Either one process per GPU (ranks launched by torchrun / Distributed.jl / MPI, joined by
+ *     gprb_comm_unique_id + gprb_comm_init_rank) or one process driving several GPUs (gprb_init_multi, one host thread
+ *     per context or sequential calls); handles of different contexts are independent.
+ *   - A GP whose factorisation failed never poisons its batch: every entry point reports per GP and carries on with
+ *     the others (the reference swallows a failed trial and continues, examples/parallel/core.jl:41-46).
  *   - There is NO CPU fallback: gprb_init fails when no sm_100 device is present.
  */
 #ifndef GPRB200_H
@@ -52,7 +56,8 @@ enum {
   GPRB_ERR_ARG = -1,      /* API misuse (null pointer, bad size, mismatched handles) */
   GPRB_ERR_CUDA = -2,     /* CUDA runtime error */
   GPRB_ERR_NODEVICE = -3, /* no sm_100 GPU visible: there is no CPU fallback */
-  GPRB_ERR_NOMEM = -4     /* device allocation failed */
+  GPRB_ERR_NOMEM = -4,    /* device allocation failed */
+  GPRB_ERR_NCCL = -5      /* NCCL error, or libnccl.so.2 not loadable (only the multi-GPU gather needs it) */
 };
 
 int gprb_version(void);               /* major*10000 + minor*100 + patch */
@@ -61,6 +66,10 @@ const char* gprb_last_error(void);    /* thread-local, never NULL */
 /* ---- context ------------------------------------------------------------------------ */
 int gprb_init(gprb_ctx** ctx, int device);
 int gprb_destroy(gprb_ctx* ctx);
+/* One process, several GPUs (the shape of SURVEY.md section 8b's `gprb_init(ctx**, ngpus, devs)`): creates one context
+ * per entry of devs (NULL = devices 0..ngpus-1) and joins them into one NCCL clique (ncclCommInitAll) for
+ * gprb_gather_multi.  ctxs receives ngpus handles; destroy each with gprb_destroy. */
+int gprb_init_multi(gprb_ctx** ctxs, int32_t ngpus, const int* devs);
 /* Device facts for roofline reporting: out[0]=SM count, out[1]=sm clock kHz, out[2]=L2 bytes, out[3]=free HBM bytes */
 int gprb_device_info(gprb_ctx* ctx, int64_t out[4]);
 
@@ -71,12 +80,23 @@ int gprb_dataset_update(gprb_dataset* ds, const double* X, int64_t ldx); /* same
  * page-locked) and the call returns after one synchronisation.  X[i] is d x n with leading dimension ldx. */
 int gprb_datasets_update(gprb_ctx* ctx, int32_t count, gprb_dataset* const* ds, const double* const* X, int64_t ldx);
 int gprb_dataset_destroy(gprb_dataset* ds);
+/* All the trial datasets of a batch in ONE device allocation: `count` matrices of identical n, d.  When the host
+ * matrices are one contiguous block (X[i+1] == X[i] + n*ldx, e.g. a 3-d array of trials) creation and every later
+ * gprb_datasets_update is one host->device copy plus one transpose launch instead of `count` of each.
+ * out receives `count` handles (each still destroyed individually; the allocation is freed with the last one). */
+int gprb_datasets_create(gprb_ctx* ctx, int32_t count, int64_t n, int32_t d, const double* const* X, int64_t ldx,
+                         gprb_dataset** out);
 
 /* ---- batch: B independent GPs, GP b uses dataset ds[b] and targets ymm[:, b] ---------- */
 /* ymm = y - m(X), n x B column-major.  All datasets must share n and d. */
 int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const double* ymm, int32_t kernel_kind,
                       gprb_batch** out);
 int gprb_batch_set_targets(gprb_batch* batch, const double* ymm); /* n x B */
+/* Fixed per-GP nugget: offset[b] is added to every diagonal entry of K_b (on top of exp(2 logNoise) + eps) in every
+ * later evaluation; NULL resets it to 0.  It is part of the matrix make_posdef! sees (tr(K)/n includes it).  Negative
+ * values are allowed - the parity tests use them to build matrices that need exactly k >= 2 jitter additions, which
+ * positive-semidefinite kernels never produce by rounding alone. */
+int gprb_batch_set_diag_offset(gprb_batch* batch, const double* offset /* B or NULL */);
 int gprb_batch_destroy(gprb_batch* batch);
 
 /* One objective evaluation per active GP (rows a5-a9 of SURVEY.md section 8a).
@@ -104,11 +124,20 @@ int gprb_eval_device(gprb_batch* batch, const double* theta_dev, double* mll_dev
 typedef struct gprb_lbfgs_opts {
   int32_t m;             /* history, default 10 */
   int32_t iterations;    /* default 1000 */
-  int32_t max_evals;     /* 0 = unlimited; deterministic replacement for time_limit */
+  int32_t max_evals;     /* 0 = unlimited; per-GP cap on f_calls + fg_calls, checked once per iteration */
   int32_t ls_iterations; /* default 1000 */
   double g_abstol;       /* default 1e-8 on ||g||_inf */
-  double time_limit;     /* seconds of wall clock for the whole batch, <= 0 = none (reference: 10 s per GP) */
+  /* time_limit (seconds, <= 0 = none).  The reference gives EVERY GP its own 10 s of CPU wall clock
+   * (Optim.Options(time_limit=10.), CPnoise.jl:41), checked once per iteration.  Two ways to express it:
+   *   cost_value == cost_grad == 0 : wall clock of the whole lock-step batch (all GPs stop together);
+   *   cost_value, cost_grad  > 0   : deterministic PER-GP virtual clock - a value-only evaluation advances a GP's clock
+   *                                  by cost_value seconds and a value+gradient evaluation by cost_grad seconds (the cost of
+   *                                  one evaluation on the machine being emulated, e.g. the reference CPU), and a GP stops
+   *                                  at the first iteration boundary where its own clock exceeds time_limit - what
+   *                                  "10 s per GP" means on the reference, reproducible and independent of GPU speed. */
+  double time_limit;
   double c_1, rho_hi, rho_lo; /* 1e-4, 0.5, 0.1 */
+  double cost_value, cost_grad; /* virtual seconds per evaluation, default 0 (see time_limit) */
 } gprb_lbfgs_opts;
 
 typedef struct gprb_opt_result {
@@ -141,12 +170,45 @@ int gprb_lbfgs_selftest(int32_t B, int32_t P, double* theta_inout, const gprb_lb
  *   var   m x B  out, NULL => mean only (the reference discards the variance: predictdynamics.jl:13) */
 int gprb_predict(gprb_batch* batch, int64_t m, const double* Xstar, int64_t xstar_stride, const double* mstar,
                  double* mu, double* var);
+/* A GP without an evaluated state (never evaluated, or its last evaluation ended with info < 0) does not block the call:
+ * its rows of mu / var come back as NaN and every other GP is predicted normally.
+ *
+ * Asynchronous form for the rollout loop (examples/utils/predictdynamics.jl:11-19): the per-step sequence
+ * "device predict -> D2H mu -> host projectv! -> H2D next states" of one group of trials overlaps the host projection of
+ * another.  gprb_predict_async enqueues the prediction of the GPs gp0 .. gp1-1 (a contiguous range of the batch, e.g. the
+ * G GPs x T/2 trials of one group) on pipeline `slot` (0 or 1; each slot has its own streams, staging and scratch) and
+ * returns at once; Xstar / mstar are indexed relative to gp0: GP gp0+k reads the test block
+ * Xstar + (k / gps_per_block)*xstar_stride - gps_per_block consecutive GPs (the G outputs of a trial, which all predict
+ * from the trial's own states) share one block, so a step uploads each trial's states once, not G times - and the prior
+ * means mstar + k*m.  Both are copied to pinned staging before the call returns, so the caller may overwrite them.  gprb_predict_wait blocks until
+ * the slot's prediction is complete and writes mu / var ((gp1-gp0) x m each; var may be NULL when want_var was 0). */
+int gprb_predict_async(gprb_batch* batch, int32_t slot, int32_t gp0, int32_t gp1, int64_t m, const double* Xstar,
+                       int64_t xstar_stride, int32_t gps_per_block, const double* mstar, int32_t want_var);
+int gprb_predict_wait(gprb_batch* batch, int32_t slot, double* mu, double* var);
+/* Device time (ms, CUDA events on the slot's stream) of the most recent completed prediction on `slot`. */
+int gprb_last_predict_ms(gprb_batch* batch, int32_t slot, double* ms);
 
 /* ---- parity taps (state after the last gprb_eval of GP b) ------------------------------ */
 int gprb_get_K(gprb_batch* batch, int32_t b, double* out /* n x n, symmetric, noise + jitter included */);
 int gprb_get_chol(gprb_batch* batch, int32_t b, double* out /* n x n upper U with K = U'U, zeros below */);
 int gprb_get_alpha(gprb_batch* batch, int32_t b, double* out /* n */);
 int gprb_get_Kinv(gprb_batch* batch, int32_t b, double* out /* n x n symmetric; needs a value+grad eval */);
+
+/* ---- multi-GPU: the final gather of per-trial results (examples/parallel/core.jl:47-56) ---------- */
+/* The path shards by trial with no data-path collective; the only exchange is one NCCL all-gather of the small per-trial
+ * result rows (theta*, mll, info, predictions) over NVLink at the end.
+ *   multi-process (one rank per GPU): rank 0 calls gprb_comm_unique_id and hands the 128 bytes to the other ranks through
+ *   whatever the host uses (a file, MPI, torch.distributed, Distributed.jl); every rank calls gprb_comm_init_rank. */
+int gprb_comm_unique_id(void* id128);
+int gprb_comm_init_rank(gprb_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+/* rows: count_local x width doubles (row-major), row_ids[k] in 0..n_rows-1 = global index (trial id) of local row k.
+ * out: n_rows x width on every rank, rows never contributed are NaN.  count_local <= ceil(n_rows / nranks) (any
+ * round-robin / block partition of the trials).  Without a communicator (single rank) it degenerates to the local scatter. */
+int gprb_gather(gprb_ctx* ctx, int32_t n_rows, int32_t width, int32_t count_local, const int32_t* row_ids,
+                const double* rows, double* out);
+/* single-process form over the contexts of gprb_init_multi: counts[g], row_ids[g], rows[g] are rank g's arguments. */
+int gprb_gather_multi(gprb_ctx* const* ctxs, int32_t ngpus, int32_t n_rows, int32_t width, const int32_t* counts,
+                      const int32_t* const* row_ids, const double* const* rows, double* out);
 
 /* ---- timing hooks for bench.py (CUDA events on the library's own streams) -------------- */
 /* Per-stage device time of the most recent gprb_eval / gprb_eval_device, milliseconds:

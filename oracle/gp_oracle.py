@@ -141,7 +141,7 @@ def chol_upper_jitter(K: np.ndarray):
 # --------------------------------------------------------------------------
 # log marginal likelihood and gradient (GPE.jl update_mll!, update_mll_and_dmll!)
 # --------------------------------------------------------------------------
-def eval_mll(X, ymm, theta, kind="se", with_grad=True, return_state=False):
+def eval_mll(X, ymm, theta, kind="se", with_grad=True, return_state=False, diag_offset=0.0):
     """One objective evaluation of one GP.
 
     X: (n, d); ymm = y - m(X): (n,); theta: (d+2,).
@@ -164,6 +164,8 @@ def eval_mll(X, ymm, theta, kind="se", with_grad=True, return_state=False):
     if not np.all(np.isfinite(K0)):
         out["info"] = -2
         return out
+    if diag_offset != 0.0:  # gprb_batch_set_diag_offset: a fixed nugget on the stored diagonal (tests of k >= 2 jitters)
+        K0[np.diag_indices_from(K0)] += diag_offset
     U, info, K = chol_upper_jitter(K0)
     out["info"] = info
     if U is None:

@@ -45,6 +45,10 @@ class LBFGSOptions:
     iterations: int = 1000
     max_evals: int = 0  # 0 = unlimited (value-only + value/grad evaluations)
     time_limit: float = math.inf
+    # > 0: deterministic virtual clock instead of wall time - every value-only evaluation costs cost_value seconds and
+    # every value+gradient evaluation cost_grad seconds (Optim checks time_limit once per iteration)
+    cost_value: float = 0.0
+    cost_grad: float = 0.0
     c_1: float = 1e-4
     rho_hi: float = 0.5
     rho_lo: float = 0.1
@@ -154,6 +158,7 @@ def lbfgs(f, fg, x0, opt: LBFGSOptions | None = None, keep_trace=False) -> LBFGS
     if g_res(g) <= opt.g_abstol:
         return LBFGSResult(x, fx, g_res(g), 0, f_calls, fg_calls, True, False, "g_abstol", trace)
 
+    vtime = opt.cost_value > 0.0 or opt.cost_grad > 0.0
     iteration = 0
     while iteration < opt.iterations:
         iteration += 1
@@ -181,15 +186,23 @@ def lbfgs(f, fg, x0, opt: LBFGSOptions | None = None, keep_trace=False) -> LBFGS
             res.update(ls_failed=True, stopped_by="linesearch")
             break
         # ---- update_g!  (value_gradient! at the new point: a second full evaluation)
-        fx, g = fg(x)
+        fx_new, g_new = fg(x)
         fg_calls += 1
-        g = np.array(g, dtype=np.float64, copy=True)
+        g_new = np.array(g_new, dtype=np.float64, copy=True)
         if keep_trace:
-            trace.append((iteration, fx, g_res(g), alpha, nev))
+            trace.append((iteration, fx_new, g_res(g_new), alpha, nev))
         # ---- assess_convergence (x/f tolerances are 0 => only exact stalls count)
         x_conv = float(np.max(np.abs(x - x_prev))) <= 0.0
-        f_conv = abs(fx - f_prev) <= 0.0
-        g_conv = g_res(g) <= opt.g_abstol
+        f_conv = abs(fx_new - f_prev) <= 0.0
+        g_conv = g_res(g_new) <= opt.g_abstol  # maximum(abs, g): NaN never converges
+        # f_increased (f_x > f_x_previous; +Inf when the re-evaluation of the accepted point failed) stops the run
+        # (allow_f_increases = false) and pick_best_x returns the PREVIOUS point; a non-finite gradient terminates
+        # too ("Terminated early due to NaN in gradient").  Either way the last good x, f, g are kept.
+        if fx_new > f_prev or not math.isfinite(fx_new) or not np.all(np.isfinite(g_new)):
+            x = x_prev
+            res.update(converged=bool(x_conv or f_conv or g_conv), stopped_by="f_increased")
+            break
+        fx, g = fx_new, g_new
         if x_conv or f_conv or g_conv:
             res.update(converged=True, stopped_by="g_abstol" if g_conv else ("x_stall" if x_conv else "f_stall"))
             break
@@ -207,7 +220,11 @@ def lbfgs(f, fg, x0, opt: LBFGSOptions | None = None, keep_trace=False) -> LBFGS
         if opt.max_evals and f_calls + fg_calls >= opt.max_evals:
             res.update(stopped_by="max_evals")
             break
-        if time.time() - t0 > opt.time_limit:
+        if vtime:
+            if f_calls * opt.cost_value + fg_calls * opt.cost_grad > opt.time_limit:
+                res.update(stopped_by="time_limit")
+                break
+        elif time.time() - t0 > opt.time_limit:
             res.update(stopped_by="time_limit")
             break
     return LBFGSResult(x, fx, g_res(g), iteration, f_calls, fg_calls, res["converged"], res["ls_failed"], res["stopped_by"], trace)
