@@ -27,6 +27,41 @@ __global__ void k_reset_jitter(double* jitter, const double* diag_off, const int
   if (k < count) jitter[list[k]] = diag_off[list[k]];
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+int make_tensor_map(CUtensorMap* map, const double* base, uint64_t rows, uint64_t cols, uint64_t gps, uint64_t col_stride_doubles,
+                    uint64_t gp_stride_doubles, uint32_t box_rows, uint32_t box_cols) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver (TMA tensor maps are required)");
+      return GPRB_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t gdim[3] = {rows, cols, gps};
+  const cuuint64_t gstride[2] = {col_stride_doubles * sizeof(double), gp_stride_doubles * sizeof(double)};
+  const cuuint32_t box[3] = {box_rows, box_cols, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return GPRB_ERR_CUDA;
+  }
+  return 0;
+}
+
+static void set_gemm_maps(GemmArgs& ga, const gprb_batch* b) {
+  ga.tm_L132 = b->tm_L132; ga.tm_L68 = b->tm_L68; ga.tm_DT132 = b->tm_DT132; ga.tm_DT68 = b->tm_DT68; ga.tm_D132 = b->tm_D132;
+}
+
 template <typename T>
 static int dev_alloc(T** p, size_t count) {
   *p = nullptr;
@@ -92,7 +127,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
 #ifdef GPRB_TIMELINE
     // debug build only: per-tile phase timestamps of this launch, averaged and printed to stderr
     static unsigned long long* tl_dev = nullptr;
-    const size_t tl_n = (size_t)count * ntiles * 8;
+    const size_t tl_n = (size_t)count * ntiles * 2 * 8;  // two half-tile CTAs per logical tile (FWD_ROW: one; the rest stays zero)
     if (!tl_dev) cudaMalloc(&tl_dev, sizeof(unsigned long long) * 8 * 65536 * 16);
     cudaMemsetAsync(tl_dev, 0, sizeof(unsigned long long) * tl_n, st);
     GemmArgs a2 = a; a2.tl = tl_dev;
@@ -126,6 +161,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   const int nv = (int)((b->n + KT - 1) / KT * KT);
   GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, b->KinvD, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG, nv};
   ga.fail = b->fail;
+  set_gemm_maps(ga, b);
   if (count > 0) {
   // Small passes are latency bound (one dependent chain of 3 J launches): they use the right-looking factorisation,
   // whose launches are short and wide, instead of the left-looking one, whose k-loops grow with the column index.
@@ -160,6 +196,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   if (prof) cudaEventRecord(b->ev[2], st);
   SolveArgs sa{b->Lm, b->Dinv, b->ymm, b->logdet_part, b->fail, b->zbuf, b->alpha, b->mll, list, ms, dstride,
                (int)b->n, (int)b->npad, J, nv};
+  sa.cluster_below = b->solve_cluster_below;
   if ((rc = launch_solve(sa, count, st))) return rc;
   ++launches;
   }
@@ -689,9 +726,22 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
       rc = cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
       break;
     }
+    // operand tensor maps of the tile GEMM: padded boxes (132 / 68 rows) x KT columns x one GP
+    if ((rc = make_tensor_map(&b->tm_L132, b->Lm, (uint64_t)b->npad, (uint64_t)b->npad, B, (uint64_t)b->npad, mat, NB + 4, KT)) ||
+        (rc = make_tensor_map(&b->tm_L68, b->Lm, (uint64_t)b->npad, (uint64_t)b->npad, B, (uint64_t)b->npad, mat, NB / 2 + 4, KT)) ||
+        (rc = make_tensor_map(&b->tm_DT132, b->DinvT, NB, (uint64_t)b->J * NB, B, NB, dinv, NB + 4, KT)) ||
+        (rc = make_tensor_map(&b->tm_DT68, b->DinvT, NB, (uint64_t)b->J * NB, B, NB, dinv, NB / 2 + 4, KT)) ||
+        (rc = make_tensor_map(&b->tm_D132, b->Dinv, NB, (uint64_t)b->J * NB, B, NB, dinv, NB + 4, KT)))
+      break;
     b->nstreams = 4;
     b->rl_max = 24;
     if (const char* ev = getenv("GPRB200_RL_MAX")) b->rl_max = atoi(ev);
+    // launches of the substitution with at most a quarter of the SM count in GPs (<= 37 on a B200: the reference's per-GP
+    // call pattern, straggler rounds of the optimiser, the stream groups of the 8-GPU strong split) run one thread-block
+    // cluster per GP; above that the one-CTA-per-GP kernel already streams at the HBM roof and clusters only add barriers
+    // (measured: 100-GP groups, 122.0 -> 129.2 ms per 400-GP step with clusters)
+    b->solve_cluster_below = ctx->sm_count / 4 + 1;
+    if (const char* ev = getenv("GPRB200_SOLVE_CLUSTER_BELOW")) b->solve_cluster_below = atoi(ev);
     if (const char* ev = getenv("GPRB200_STREAMS")) b->nstreams = std::max(1, std::min(MAX_STREAMS, atoi(ev)));
     for (int s = 0; s < MAX_STREAMS && !rc; ++s) {
       if ((e = cudaStreamCreateWithFlags(&b->stream[s], cudaStreamNonBlocking)) != cudaSuccess ||
@@ -897,7 +947,15 @@ static int predict_enqueue(gprb_batch* b, int slot, int gp0, int gp1, int64_t m,
     b->ctx->launches++;
   } else {
     if ((rc = ensure_dev(&sl.pmupart, &sl.pmupart_cap, (size_t)count * J * PT))) return rc;
-    if (want_var && (rc = ensure_dev(&sl.pT, &sl.pT_cap, (size_t)count * b->npad * PT))) return rc;
+    if (want_var) {
+      if ((rc = ensure_dev(&sl.pT, &sl.pT_cap, (size_t)count * b->npad * PT))) return rc;
+      if (sl.tm_T_cap != sl.pT_cap) {  // (re)allocated: the right-hand-side block [GP][row r = k][PT test columns], box = 68 columns x KT rows
+        if ((rc = make_tensor_map(&sl.tm_T68, sl.pT, PT, (uint64_t)b->npad, sl.pT_cap / ((size_t)b->npad * PT), PT, (uint64_t)b->npad * PT,
+                                  NB / 2 + 4, KT)))
+          return rc;
+        sl.tm_T_cap = sl.pT_cap;
+      }
+    }
     const int nv = (int)((b->n + KT - 1) / KT * KT);
     for (int64_t s0 = 0; s0 < m; s0 += PT) {
       PredictTileArgs ta{b->Xtptr, b->theta, b->alpha, sl.pX, mstar ? sl.pms : nullptr, want_var ? sl.pT : nullptr, sl.pmupart,
@@ -913,10 +971,13 @@ static int predict_enqueue(gprb_batch* b, int slot, int gp0, int gp1, int64_t m,
         GemmArgs ga{b->Lm, b->DinvT, b->Dinv, nullptr, b->Lm, b->KinvD, nullptr, b->npad * b->npad, (int64_t)J * NB * NB,
                     (int)b->npad, J, 0, GEMM_FWD_ROW, nv};
         ga.Tm = sl.pT; ga.t_stride = b->npad * PT; ga.ldt = PT; ga.t_gp_off = gp0;
+        set_gemm_maps(ga, b);
+        ga.tm_T68 = sl.tm_T68;
         ga.ncols = ta.mc;
         ga.fail = sl.mask;  // tiles of a GP without state exit at once
-        // few GPs (large n, or the reference's single-GP call pattern): narrower tiles, so that a launch still fills the SMs
-        ga.colw = count >= b->ctx->sm_count ? PT : (2 * count >= b->ctx->sm_count ? PT / 2 : PT / 4);
+        // right-hand-side tiles are 64 test columns wide (two CTAs per SM); few GPs (large n, or the reference's single-GP
+        // call pattern): 32-column tiles, so that a launch still puts a CTA on every SM
+        ga.colw = (int64_t)count * ((ta.mc + 63) / 64) >= b->ctx->sm_count ? 64 : 32;
         const int ntl = (ta.mc + ga.colw - 1) / ga.colw;
         // the GPs are dealt over the stream groups: the dependent chain of J launches of one group fills the wave
         // tails of the others (`count` tiles per launch are not a multiple of the SM count)

@@ -1,5 +1,6 @@
 // Shared definitions for libgprb200: handles, launch geometry, sm_100a PTX helpers.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,6 +22,14 @@ constexpr int MAX_STREAMS = 8; // the GPs of one call are split over up to this 
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+// TMA tensor map over a batched column-major fp64 array viewed as [dim2 = GP][dim1 = column][dim0 = row]:
+// one cp.async.bulk.tensor request (SASS UTMALDG) then lands a whole k-chunk of `box_cols` columns x `box_rows` rows in
+// shared memory.  box_rows is the PADDED row count (132 / 68 for 128- / 64-row operands): the box simply reads 4 rows
+// more than the operand needs (zero-filled where that leaves the array), which makes the smem pitch equal to the
+// bank-conflict-free padded pitch of the DMMA fragment loads - a tiled box has no pitch of its own.
+int make_tensor_map(CUtensorMap* map, const double* base, uint64_t rows, uint64_t cols, uint64_t gps, uint64_t col_stride_doubles,
+                    uint64_t gp_stride_doubles, uint32_t box_rows, uint32_t box_cols);
 
 #define GPRB_CUDA(call)                                                        \
   do {                                                                         \
@@ -91,6 +100,8 @@ struct gprb_dataset {
 struct gprb_predict_slot {
   double* pX = nullptr; double* pms = nullptr; double* pmu = nullptr; double* pvar = nullptr;  // device
   double* pT = nullptr; double* pmupart = nullptr; double* pq = nullptr;
+  CUtensorMap tm_T68;          // pT [count][npad][PT], re-encoded whenever pT is (re)allocated
+  size_t tm_T_cap = 0;
   int32_t* pcount = nullptr;   // [cap_gps] arrival counters of the split GEMV path (zero between calls)
   int32_t* mask = nullptr;     // device [B]: 1 = GP has no evaluated state (outputs NaN)
   size_t pX_cap = 0, pms_cap = 0, pmu_cap = 0, pvar_cap = 0, pT_cap = 0, pmupart_cap = 0, pq_cap = 0, pcount_cap = 0;
@@ -145,6 +156,7 @@ struct gprb_batch {
   cudaStream_t stream[gprb::MAX_STREAMS] = {};
   int nstreams = 1;
   int rl_max = 24;                // passes with at most this many GPs use the right-looking (low-latency) factorisation
+  int solve_cluster_below = 0;    // passes with fewer GPs than this use k_solve_cluster (GPRB200_SOLVE_CLUSTER_BELOW, default SM count)
   cudaEvent_t ev[8] = {};
   cudaEvent_t join[gprb::MAX_STREAMS] = {};
   bool profiling = false;
@@ -159,6 +171,10 @@ struct gprb_batch {
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // prediction pipelines (scratch allocated on first use and kept, grow-only): slot s runs on stream[4s .. 4s+3]
   gprb_predict_slot ps[2];
+  // TMA tensor maps of the tile GEMM's operands (encoded once per batch; box = padded rows x KT columns x 1 GP)
+  CUtensorMap tm_L132, tm_L68;     // Lm  [B][npad][npad]
+  CUtensorMap tm_DT132, tm_DT68;   // DinvT [B][J*128][128]
+  CUtensorMap tm_D132;             // Dinv  [B][J*128][128]
   std::vector<cudaEvent_t> gemm_ev;  // profiling: start/stop pairs around every tile-GEMM launch
   int gemm_ev_used = 0;
   std::vector<double> gemm_ms;  // per tile-GEMM launch time of the last profiled evaluation, launch order
@@ -205,6 +221,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 3-D tiled TMA load (SASS UTMALDG): the box at element coordinates (c0 = row, c1 = column, c2 = GP) of the tensor map
+// lands densely at dst (128-byte aligned); completion is counted in bytes on `bar` (always the full box, out-of-range
+// elements arrive as zeros).
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                : "memory");
 }
 // Order generic-proxy smem writes before later async-proxy (TMA) accesses to the same smem.

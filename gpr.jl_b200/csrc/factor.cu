@@ -2,6 +2,11 @@
 // triangular solves for alpha = K^-1 (y - m) with the log-marginal-likelihood value
 // (SURVEY.md section 8a rows a6, a7).  The O(n^3) work lives in tilegemm.cu; these are the serial
 // O(n * 128^2) / O(n^2) pieces between the GEMM launches.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -209,6 +214,16 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
 // ---------------------------------------------------------------------------------------------
 constexpr int SOLVE_THREADS = 512;
 
+// rows rb, rb + 32, rb + 64, rb + 96 of one 128-row block of column Lcol against alpha (rows >= nv are padding)
+__device__ __forceinline__ void backward_block(const double* Lcol, const double* al, int rb, int nv, double& a0, double& a1) {
+  const double l0 = rb < nv ? Lcol[rb] : 0.0, l1 = rb + 32 < nv ? Lcol[rb + 32] : 0.0;
+  const double l2 = rb + 64 < nv ? Lcol[rb + 64] : 0.0, l3 = rb + 96 < nv ? Lcol[rb + 96] : 0.0;
+  if (rb < nv) a0 = fma(l0, al[rb], a0);
+  if (rb + 32 < nv) a1 = fma(l1, al[rb + 32], a1);
+  if (rb + 64 < nv) a0 = fma(l2, al[rb + 64], a0);
+  if (rb + 96 < nv) a1 = fma(l3, al[rb + 96], a1);
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* z = reinterpret_cast<double*>(smem_raw);  // [npad]
@@ -255,18 +270,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
     __syncthreads();
   }
 
-  // ---- backward: alpha_j = Dinv_j^T (z_j - sum_{i>j} L(i,j)^T alpha_i); warp per column, lanes over rows
+  // ---- backward: alpha_j = Dinv_j^T (z_j - sum_{i>j} L(i,j)^T alpha_i); warp per column, lanes over rows.
+  // Canonical summation order (shared with k_solve_cluster, which receives alpha_i block by block from i = J-1 down):
+  // block rows i = J-1 .. jb+1, inside a block the lane's rows lane, +32, +64, +96 alternate between two accumulators.
   for (int jb = J - 1; jb >= 0; --jb) {
-    const int rbeg = (jb + 1) * NB;
     for (int c = warp; c < NB; c += SOLVE_THREADS / 32) {
       const double* Lcol = L + (int64_t)(jb * NB + c) * npad;
       double a0 = 0.0, a1 = 0.0;
-      int r = rbeg + lane;
-      for (; r + 32 < nv; r += 64) {
-        a0 = fma(Lcol[r], al[r], a0);
-        a1 = fma(Lcol[r + 32], al[r + 32], a1);
+      if (J - 1 > jb) backward_block(Lcol, al, (J - 1) * NB + lane, nv, a0, a1);  // only the last block row is ragged
+#pragma unroll 4
+      for (int i = J - 2; i > jb; --i) {  // full blocks: eight and more independent loads in flight per lane
+        const int rb = i * NB + lane;
+        const double l0 = Lcol[rb], l1 = Lcol[rb + 32], l2 = Lcol[rb + 64], l3 = Lcol[rb + 96];
+        a0 = fma(l0, al[rb], a0);
+        a1 = fma(l1, al[rb + 32], a1);
+        a0 = fma(l2, al[rb + 64], a0);
+        a1 = fma(l3, al[rb + 96], a1);
       }
-      for (; r < nv; r += 32) a0 = fma(Lcol[r], al[r], a0);
       double s = a0 + a1;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -289,6 +309,144 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
   for (int r = tid; r < (int)npad; r += SOLVE_THREADS) { zout[r] = z[r]; aout[r] = al[r]; }
 
   // ---- mll = -1/2 (z'z + 2 sum log L_ii + n log 2pi)      (ymm' alpha == z'z)
+  if (warp == 0) {
+    double s = 0.0;
+    for (int r = lane; r < g.n; r += 32) s = fma(z[r], z[r], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+      double ld = 0.0;
+      for (int jb = 0; jb < J; ++jb) ld += g.logdet_part[(int64_t)gp * J + jb];
+      g.mll[gp] = -0.5 * (s + 2.0 * ld + g.n * 1.8378770664093453);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// The same substitution for passes with fewer GPs than SMs (the reference's one-GP-at-a-time call pattern, straggler
+// rounds of the batched optimiser, the 50 GPs per GPU of the 8-GPU strong split): one GP = one thread-block CLUSTER
+// of C CTAs instead of one CTA.  A single CTA streams the 32 MB factor of an n = 2000 GP at ~25 GB/s (latency bound,
+// ~1.1 ms); C CTAs stream it C times as fast.
+//   forward   block row i belongs to CTA i mod C; its thread (row, k-partition) keeps the four running sums of
+//             k_solve in registers and adds block column j when z_j arrives; the owner of block row j finishes z_j with
+//             the inverted diagonal block and writes it into every CTA's copy through distributed shared memory
+//   backward  block column j belongs to CTA j mod C; alpha_i arrives from i = J-1 down
+// Every thread adds its terms in exactly the order of k_solve, so both kernels give bit-identical results (a GP's
+// numbers do not depend on how many GPs share its pass - tests/test_gpu_parity.py::test_results_do_not_depend_...).
+// ---------------------------------------------------------------------------------------------------------
+template <int MAXOWN>  // block rows / columns per CTA: J <= MAXOWN * C
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve_cluster(SolveArgs g, int C) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* z = reinterpret_cast<double*>(smem_raw);  // [npad] full copies, filled block by block by the owners
+  double* al = z + g.npad;                            // [npad]
+  double* red = al + g.npad;                          // [4][NB]
+  double* rv = red + 4 * NB;                          // [NB]
+  const int q = (int)cluster.block_rank();
+  const int gp = g.list ? g.list[blockIdx.y] : blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t npad = g.npad;
+  const int J = g.J, nv = g.nv;
+  if (g.fail[gp] != 0) {  // uniform over the cluster: nobody reaches a cluster barrier
+    if (q == 0 && tid == 0) g.mll[gp] = -__longlong_as_double(0x7ff0000000000000LL);
+    return;
+  }
+  const double* L = g.Lm + (int64_t)gp * g.mat_stride;
+  const double* Dinv = g.Dinv + (int64_t)gp * g.dinv_stride;
+  const double* y = g.ymm + (int64_t)gp * npad;
+  const int row = tid & (NB - 1), part = tid >> 7;
+
+  // ---- forward
+  double fa[MAXOWN][4];
+#pragma unroll
+  for (int o = 0; o < MAXOWN; ++o) fa[o][0] = fa[o][1] = fa[o][2] = fa[o][3] = 0.0;
+  for (int j = 0; j < J; ++j) {
+    if (q == j % C) {  // finish z_j (same reduction tree as k_solve) and hand it to every CTA of the cluster
+      const int o = j / C;
+      double s4 = 0.0;
+#pragma unroll
+      for (int oo = 0; oo < MAXOWN; ++oo)
+        if (oo == o) s4 = (fa[oo][0] + fa[oo][1]) + (fa[oo][2] + fa[oo][3]);
+      red[part * NB + row] = s4;
+      __syncthreads();
+      if (tid < NB) rv[tid] = y[j * NB + tid] - ((red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]));
+      __syncthreads();
+      const double* Dj = Dinv + (int64_t)j * NB * NB;
+      double s = 0.0;
+      for (int kk = part; kk <= row; kk += 4) s = fma(Dj[row + kk * NB], rv[kk], s);
+      red[part * NB + row] = s;
+      __syncthreads();
+      if (tid < NB) {
+        const double zv = (red[tid] + red[NB + tid]) + (red[2 * NB + tid] + red[3 * NB + tid]);
+        for (int r = 0; r < C; ++r) cluster.map_shared_rank(z, r)[j * NB + tid] = zv;
+      }
+    }
+    cluster.sync();  // z_j visible everywhere (release / acquire at cluster scope)
+#pragma unroll
+    for (int o = 0; o < MAXOWN; ++o) {
+      const int i = q + o * C;
+      if (i < J && i > j && i * NB + row < nv) {  // padding rows keep z = 0 (kend = 0 in k_solve)
+        const double* Lrow = L + (int64_t)i * NB + row + (int64_t)(j * NB + part) * npad;
+        const double* zk = z + j * NB + part;
+        double l[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) l[t] = Lrow[(int64_t)(4 * t) * npad];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) fa[o][t & 3] = fma(l[t], zk[4 * t], fa[o][t & 3]);
+      }
+    }
+  }
+
+  // ---- backward
+  double ba[MAXOWN][NB / (SOLVE_THREADS / 32)][2];
+#pragma unroll
+  for (int o = 0; o < MAXOWN; ++o)
+#pragma unroll
+    for (int cc = 0; cc < NB / (SOLVE_THREADS / 32); ++cc) ba[o][cc][0] = ba[o][cc][1] = 0.0;
+  for (int i = J - 1; i >= 0; --i) {
+    if (q == i % C) {
+      const int o = i / C;
+#pragma unroll
+      for (int cc = 0; cc < NB / (SOLVE_THREADS / 32); ++cc) {
+        const int c = warp + cc * (SOLVE_THREADS / 32);
+        double s = 0.0;
+#pragma unroll
+        for (int oo = 0; oo < MAXOWN; ++oo)
+          if (oo == o) s = ba[oo][cc][0] + ba[oo][cc][1];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) rv[c] = z[i * NB + c] - s;
+      }
+      __syncthreads();
+      const double* Dj = Dinv + (int64_t)i * NB * NB;
+      for (int c = warp; c < NB; c += SOLVE_THREADS / 32) {
+        double s = 0.0;
+        for (int kk = c + lane; kk < NB; kk += 32) s = fma(Dj[kk + c * NB], rv[kk], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane < C) cluster.map_shared_rank(al, lane)[i * NB + c] = s;  // lane r writes CTA r's copy
+      }
+    }
+    cluster.sync();
+#pragma unroll
+    for (int o = 0; o < MAXOWN; ++o) {
+      const int j = q + o * C;
+      if (j < J && j < i) {
+#pragma unroll
+        for (int cc = 0; cc < NB / (SOLVE_THREADS / 32); ++cc) {
+          const int c = warp + cc * (SOLVE_THREADS / 32);
+          backward_block(L + (int64_t)(j * NB + c) * npad, al, i * NB + lane, nv, ba[o][cc][0], ba[o][cc][1]);
+        }
+      }
+    }
+  }
+
+  if (q != 0) return;
+  double* zout = g.zbuf + (int64_t)gp * npad;
+  double* aout = g.alpha + (int64_t)gp * npad;
+  for (int r = tid; r < (int)npad; r += SOLVE_THREADS) { zout[r] = z[r]; aout[r] = al[r]; }
   if (warp == 0) {
     double s = 0.0;
     for (int r = lane; r < g.n; r += 32) s = fma(z[r], z[r], s);
@@ -326,6 +484,29 @@ int launch_solve(const SolveArgs& a, int count, cudaStream_t stream) {
   if (smem > 227 * 1024) {
     set_error("k_solve: n too large for the shared-memory resident substitution (npad <= 14000)");
     return GPRB_ERR_ARG;
+  }
+  // fewer GPs than SMs: one cluster of C CTAs per GP (bit-identical results, see k_solve_cluster)
+  const int C = std::min(8, a.J);
+  const int maxown = (a.J + C - 1) / C;
+  if (count < a.cluster_below && C >= 2 && maxown <= 4) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C, count);
+    cfg.blockDim = dim3(SOLVE_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t ec;
+#define GPRB_SOLVE_CLUSTER(M)                                                                                       \
+    ec = cudaFuncSetAttribute(k_solve_cluster<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (ec == cudaSuccess) ec = cudaLaunchKernelEx(&cfg, k_solve_cluster<M>, a, C);
+    if (maxown == 1) { GPRB_SOLVE_CLUSTER(1) } else if (maxown == 2) { GPRB_SOLVE_CLUSTER(2) } else { GPRB_SOLVE_CLUSTER(4) }
+#undef GPRB_SOLVE_CLUSTER
+    if (ec != cudaSuccess) return cuda_fail(ec, "k_solve_cluster launch", __FILE__, __LINE__);
+    return 0;
   }
   cudaError_t e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_solve)", __FILE__, __LINE__);

@@ -1,5 +1,6 @@
 // Launcher prototypes of the libgprb200 CUDA stages (host-callable, defined in the .cu files).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,11 +26,13 @@ struct GemmArgs {
   int64_t t_stride = 0;
   int ldt = 0;
   int ncols = 128;      // valid test columns of the block (< 128: compact warp layout skips the padding columns)
-  int colw = 128;       // columns per FWD_ROW tile (128, 64 or 32): tile bx owns columns bx*colw .. of the block
+  int colw = 64;        // columns per FWD_ROW tile (64 or 32): tile bx owns columns bx*colw .. of the block
   int gp_off = 0;       // first GP of this launch when `list` is null (stream groups of gprb_predict)
   int t_gp_off = 0;     // GEMM_FWD_ROW: Tm is indexed by gp - t_gp_off (the right-hand-side blocks of a GP range start at its first GP)
   const int32_t* fail = nullptr;     // [B] per-GP failure flag: tiles of a GP whose factorisation already broke down exit at once
   unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)
+  // TMA tensor maps of the operands (gprb_batch / gprb_predict_slot own them): box = 132 or 68 padded rows x KT columns
+  CUtensorMap tm_L132, tm_L68, tm_DT132, tm_DT68, tm_D132, tm_T68;
 };
 
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream);
@@ -78,6 +81,7 @@ struct SolveArgs {
   int64_t mat_stride, dinv_stride;
   int n, npad, J;
   int nv;
+  int cluster_below = 0;      // passes with fewer GPs than this run one thread-block cluster per GP (k_solve_cluster)
 };
 int launch_solve(const SolveArgs& a, int count, cudaStream_t stream);
 

@@ -1,32 +1,38 @@
-# GPRB200.jl - thin ccall shim that keeps the GP surface GPR.jl's experiments call and routes it to libgprb200.so.
+# GPRB200.jl - routes the GP calls of GPR.jl's experiments to libgprb200.so WITHOUT changing their types.
 #
 # NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain.  The tested contract is the C ABI
 # (include/gprb200.h, exercised through ctypes by tests/); every ccall below mirrors one prototype of that header
-# one-to-one, and gpr.jl_b200/lib.py is the executable twin of this file.
+# one-to-one (tests/test_julia_shim_signatures.py parses this file and checks every ccall tuple against the header),
+# and gpr.jl_b200/lib.py + gp.py are the executable twin.  Names and signatures of GaussianProcesses.jl 0.12.4
+# internals (GPE type parameters, alloc_cK, the 8-argument GPE constructor, init_precompute) are written from the
+# published source of that version (Manifest.toml:409-413) and could not be compiled here.
 #
-# Drop-in use inside the reference (paths relative to the GPR.jl checkout):
+# Drop-in mechanism: GaussianProcesses.jl's own extension point for the linear-algebra back end is the covariance
+# strategy (`GPE(...; covstrat)`, used by its sparse approximations).  `B200Covariance <: CovarianceStrategy` keeps the
+# object a real `GaussianProcesses.GPE`, so the reference's typed call sites work unchanged:
+#     gps = Vector{GPE}()                                              examples/maximal_coordinates/CPnoise.jl:35
+#     predictdynamics(mechanism, gps::Vector{<:GPE}, x0, steps, getvω)   examples/utils/predictdynamics.jl:7
+# Nothing is exported that GaussianProcesses / Optim export (`using GaussianProcesses, GPRB200` has no clashes).
 #
-#     # examples/maximal_coordinates/CPnoise.jl:35-43, unchanged except for the module prefix
-#     using GPRB200                       # instead of `using GaussianProcesses` for the four calls below
-#     kernel = SEArd(log.(params[2:end]), log(params[1]))
-#     gp = GP(xtrain_old, yi, MeanZero(), kernel)                     # or MeanDynamics(...) from src/mDynamics.jl
-#     GPRB200.optimize!(gp, LBFGS(linesearch = BackTracking(order=2)), Optim.Options(time_limit=10.))
-#     μ = predict_y(gp, obs)[1][1]                                    # examples/utils/predictdynamics.jl:13
-#
-# and, batched (what replaces the `Threads.@threads for jobid` loop of examples/parallel/core.jl:28):
-#
-#     gps = [GPE(X_t, y_tk, mean_tk, SEArd(...)) for t in trials for k in outputs]     # no evaluation yet
-#     batch = GPBatch(gps)                                            # uploads each distinct X once
-#     GPRB200.optimize!(batch, LBFGS(linesearch = BackTracking(order=2)), Optim.Options(iterations=1000))
-#     μ, σ² = predict_y(batch, Xstar)                                 # B × m
+# Per-GP flavour - the ONLY edit in an experiment body (CPnoise.jl:40): the constructor gets the strategy
+#     kernel = SEArd(log.(params[2:end]), log(params[1]))                          # :38 unchanged
+#     gp = GP(xtrain_old, yi, mean, kernel, B200Covariance())                      # :40  (+ one argument)
+#     GaussianProcesses.optimize!(gp, LBFGS(linesearch = BackTracking(order=2)), Optim.Options(time_limit=10.))   # :41 unchanged
+#     μ = predict_y(gp, obs)[1][1]                                                 # predictdynamics.jl:13 unchanged
+# Batched flavour (what replaces the `Threads.@threads for jobid` loop of examples/parallel/core.jl:28):
+#     gps = [GPE(X_t, y_tk, mean_tk, SEArd(...), -2.0, B200Covariance()) for t in trials for k in outputs]   # no evaluation yet
+#     GaussianProcesses.optimize!(gps, LBFGS(linesearch = BackTracking(order=2)), Optim.Options(time_limit=10.))  # ONE gprb_optimize
+#     predictdynamics(mechanism, gps[(t-1)*G+1:t*G], x0, steps, getvω)            # unchanged; the G predict_y calls of a step share one device call
 module GPRB200
 
 using Libdl
-import GaussianProcesses                       # only for the Mean plug-in protocol and the kernel parameter types
-import GaussianProcesses: Mean, MeanZero, SEArd, Mat12Ard, Mat32Ard, Mat52Ard, get_params, set_params!, num_params
+import GaussianProcesses
+import GaussianProcesses: GPE, Mean, MeanZero, Kernel, SEArd, Mat12Ard, Mat32Ard, Mat52Ard, CovarianceStrategy, KernelData, EmptyData,
+                          get_params, set_params!, num_params
 import Optim
+import PDMats
 
-export GPE, GP, GPBatch, optimize!, predict_y, update_mll!, update_mll_and_dmll!, SEArd, MeanZero
+export B200Covariance, GPBatch, params_to_theta, theta_to_params, gather_results
 
 const LIB = get(ENV, "GPRB200_LIB", joinpath(@__DIR__, "..", "libgprb200.so"))
 
@@ -55,60 +61,71 @@ kernel_kind(::Mat12Ard) = Cint(1)
 kernel_kind(::Mat32Ard) = Cint(2)
 kernel_kind(::Mat52Ard) = Cint(3)
 
-# ---- GPE: the fields the reference's callers read (gp.x, gp.y, gp.mean, gp.kernel, gp.logNoise, gp.mll, gp.dmll, gp.alpha)
-mutable struct GPE
-    x::Matrix{Float64}          # d × n, one CState per column (src/CState.jl:20)
-    y::Vector{Float64}
-    mean::Mean
-    kernel
-    logNoise::Float64
-    dim::Int
-    nobs::Int
-    mll::Float64
-    dmll::Vector{Float64}
-    info::Int32
-    batch::Any                  # owning GPBatch
-    slot::Int
+# ---- the covariance strategy -----------------------------------------------------------------------------------------
+"Covariance strategy that keeps K, its factor and alpha in HBM (libgprb200.so) instead of a host PDMat."
+struct B200Covariance <: CovarianceStrategy end
+
+# gp.cK is never read by the reference's callers; a 1-byte placeholder satisfies the field type (no n x n host allocation,
+# no n x n x d distance stack: KernelData is EmptyData)
+GaussianProcesses.alloc_cK(::B200Covariance, nobs::Int) = PDMats.ScalMat(nobs, 1.0)
+
+const B200GPE = GPE{<:AbstractMatrix,<:AbstractVector,<:Mean,<:Kernel,<:B200Covariance}
+
+"`GPE(X, y, mean, kernel, logNoise, B200Covariance())`: a GaussianProcesses.GPE whose linear algebra lives on the B200 (no evaluation yet)."
+GaussianProcesses.GPE(x::AbstractMatrix, y::AbstractVector, mean::Mean, kernel::Kernel, logNoise::Real, cs::B200Covariance) =
+    GPE(Matrix{Float64}(x), Vector{Float64}(y), mean, kernel, Float64(logNoise), cs, EmptyData(), GaussianProcesses.alloc_cK(cs, length(y)))
+
+"`GP(X, y, mean, kernel, B200Covariance())`: construct + initial update_mll!, like GaussianProcesses.GP (CPnoise.jl:40)."
+function GaussianProcesses.GP(x::AbstractMatrix, y::AbstractVector, mean::Mean, kernel::Kernel, cs::B200Covariance; logNoise::Real = -2.0)
+    gp = GPE(x, y, mean, kernel, logNoise, cs)
+    GaussianProcesses.update_mll!(gp)
+    gp
 end
-GPE(X::AbstractMatrix, y::AbstractVector, mean::Mean, kernel, logNoise::Real = -2.0) =
-    GPE(Matrix{Float64}(X), Vector{Float64}(y), mean, kernel, Float64(logNoise), size(X, 1), size(X, 2), NaN, Float64[], 0, nothing, 0)
 
 # GaussianProcesses.get_params order: [logNoise; mean params; kernel params] - the reference's means have none (src/mDynamics.jl:29-31)
-params(gp::GPE) = vcat(gp.logNoise, get_params(gp.mean), get_params(gp.kernel))
-function setparams!(gp::GPE, θ::AbstractVector)
-    gp.logNoise = θ[1]
-    nm = num_params(gp.mean)
-    nm > 0 && set_params!(gp.mean, θ[2:1+nm])
-    set_params!(gp.kernel, θ[2+nm:end])
-end
+theta_of(gp::GPE) = Vector{Float64}(get_params(gp))
 
-# ---- GPBatch ---------------------------------------------------------------------------------------------------------
+# ---- GPBatch: the device residence of one or many GPEs ----------------------------------------------------------------
 mutable struct GPBatch
     gps::Vector{GPE}
     handle::Ptr{Cvoid}
     datasets::Vector{Ptr{Cvoid}}
     B::Int; n::Int; d::Int; P::Int
+    # shared prediction cache of one rollout step: the G predict_y(gp, obs) calls of predictdynamics.jl:13 hit one device call
+    cache_key::Matrix{Float64}
+    cache_mu::Matrix{Float64}
+    cache_var::Matrix{Float64}
 end
 
-function GPBatch(gps::Vector{GPE})
+# gp -> (batch, slot); weak, so dropping the GPEs frees the device memory through the batch finalizer
+const RESIDENT = WeakKeyDict{GPE,Tuple{GPBatch,Int}}()
+
+function GPBatch(gps::Vector{<:GPE})
     ctx = context()
     d, n = gps[1].dim, gps[1].nobs
     B = length(gps)
-    seen = IdDict{Any,Ptr{Cvoid}}()
-    handles = Vector{Ptr{Cvoid}}(undef, B)
-    for (b, gp) in enumerate(gps)
-        handles[b] = get!(seen, gp.x) do                 # GPs of one trial share the same X object => one upload
-            h = Ref{Ptr{Cvoid}}(C_NULL)
-            check(ccall((:gprb_dataset_create, LIB), Cint, (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Int64, Ref{Ptr{Cvoid}}),
-                        ctx, n, d, gp.x, d, h))
-            h[]
-        end
+    # all distinct training sets of the batch in ONE device allocation, uploaded as one contiguous block
+    uniq = IdDict{Any,Int}()
+    for gp in gps
+        get!(uniq, gp.x, length(uniq) + 1)
     end
+    T = length(uniq)
+    block = Array{Float64,3}(undef, d, n, T)
+    for (x, t) in uniq
+        block[:, :, t] = x
+    end
+    ptrs = [pointer(block, (t - 1) * d * n + 1) for t in 1:T]
+    dsh = Vector{Ptr{Cvoid}}(undef, T)
+    GC.@preserve block begin
+        check(ccall((:gprb_datasets_create, LIB), Cint, (Ptr{Cvoid}, Int32, Int64, Int32, Ptr{Ptr{Float64}}, Int64, Ptr{Ptr{Cvoid}}),
+                    ctx, T, n, d, ptrs, d, dsh))
+    end
+    handles = [dsh[uniq[gp.x]] for gp in gps]
     # m(X) does not depend on θ: evaluate once per training set, column by column across the GPs of a trial so the shared
     # MDCache (src/mDynamics.jl:6-11,42) hits for the other G-1 outputs.  Only y - m(X) goes to the device.
     ymm = Matrix{Float64}(undef, n, B)
-    for xs in unique(objectid(gp.x) for gp in gps)
-        members = [b for b in 1:B if objectid(gps[b].x) == xs]
+    for (x, _) in uniq
+        members = [b for b in 1:B if gps[b].x === x]
         for j in 1:n, b in members
             ymm[j, b] = gps[b].y[j] - GaussianProcesses.mean(gps[b].mean, gps[b].x[:, j])
         end
@@ -116,9 +133,9 @@ function GPBatch(gps::Vector{GPE})
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:gprb_batch_create, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
                 ctx, B, handles, ymm, kernel_kind(gps[1].kernel), h))
-    batch = GPBatch(gps, h[], collect(values(seen)), B, n, d, d + 2)
+    batch = GPBatch(Vector{GPE}(gps), h[], dsh, B, n, d, d + 2, zeros(0, 0), zeros(0, 0), zeros(0, 0))
     for (b, gp) in enumerate(gps)
-        gp.batch, gp.slot = batch, b
+        RESIDENT[gp] = (batch, b)
     end
     finalizer(batch) do bt
         ccall((:gprb_batch_destroy, LIB), Cint, (Ptr{Cvoid},), bt.handle)
@@ -127,9 +144,15 @@ function GPBatch(gps::Vector{GPE})
     batch
 end
 
-thetas(batch::GPBatch) = reduce(hcat, params.(batch.gps))          # P × B, column per GP: the layout gprb_eval takes
+"The batch a GPE lives in (a batch of one is created on demand: the reference's per-GP call pattern)."
+function residence(gp::GPE)
+    haskey(RESIDENT, gp) || GPBatch(GPE[gp])
+    RESIDENT[gp]
+end
 
-"One objective evaluation per GP: update_mll! (grad=false) / update_mll_and_dmll! (grad=true)."
+thetas(batch::GPBatch) = reduce(hcat, theta_of.(batch.gps))          # P × B, column per GP: the layout gprb_eval takes
+
+"One objective evaluation per active GP of the batch; writes mll / dmll / alpha back into the GPE fields the callers read."
 function evaluate!(batch::GPBatch; θ::Matrix{Float64} = thetas(batch), grad::Bool = true, active::Union{Nothing,Vector{UInt8}} = nothing)
     mll = fill(NaN, batch.B)
     g = grad ? fill(NaN, batch.P, batch.B) : nothing
@@ -140,25 +163,48 @@ function evaluate!(batch::GPBatch; θ::Matrix{Float64} = thetas(batch), grad::Bo
     end
     for (b, gp) in enumerate(batch.gps)
         (active === nothing || active[b] != 0) || continue
-        gp.mll, gp.info = mll[b], info[b]
-        grad && (gp.dmll = g[:, b])
+        gp.mll = mll[b]; gp.target = mll[b]                       # no priors are set anywhere in the reference
+        if grad
+            gp.dmll = g[:, b]; gp.dtarget = g[:, b]
+        end
+        info[b] < 0 && throw(PDMats.PosDefException(Int(info[b])))   # get_optim_target's catch branch turns this into +Inf
     end
+    batch.cache_key = zeros(0, 0)
     mll, g, info
 end
-update_mll!(gp::GPE) = (evaluate!(gp.batch; grad = false); gp)
-update_mll_and_dmll!(gp::GPE) = (evaluate!(gp.batch; grad = true); gp)
 
-"GP(X, y, mean, kernel): construct + initial update_mll! (GaussianProcesses.GP), a batch of one."
-function GP(X::AbstractMatrix, y::AbstractVector, mean::Mean, kernel, logNoise::Real = -2.0)
-    gp = GPE(X, y, mean, kernel, logNoise)
-    evaluate!(GPBatch([gp]); grad = false)
+function only_active(batch::GPBatch, slot::Int)
+    a = zeros(UInt8, batch.B)
+    a[slot] = 1
+    a
+end
+
+# the two evaluation entry points GaussianProcesses.optimize! / GP(...) reach (GPE.jl: update_mll!, update_mll_and_dmll!)
+function GaussianProcesses.update_mll!(gp::B200GPE; kwargs...)
+    batch, slot = residence(gp)
+    evaluate!(batch; grad = false, active = batch.B == 1 ? nothing : only_active(batch, slot))
     gp
+end
+function GaussianProcesses.update_mll_and_dmll!(gp::B200GPE, precomp...; kwargs...)
+    batch, slot = residence(gp)
+    evaluate!(batch; grad = true, active = batch.B == 1 ? nothing : only_active(batch, slot))
+    gp
+end
+GaussianProcesses.init_precompute(gp::B200GPE) = nothing     # no n x n host work buffer
+
+"gp.alpha on demand (the field is filled lazily: the rollout never reads it)."
+function alpha!(gp::B200GPE)
+    batch, slot = residence(gp)
+    a = Vector{Float64}(undef, batch.n)
+    check(ccall((:gprb_get_alpha, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), batch.handle, slot - 1, a))
+    gp.alpha = a
 end
 
 # ---- optimize! -------------------------------------------------------------------------------------------------------
 struct LbfgsOpts                 # gprb_lbfgs_opts
     m::Int32; iterations::Int32; max_evals::Int32; ls_iterations::Int32
     g_abstol::Float64; time_limit::Float64; c_1::Float64; rho_hi::Float64; rho_lo::Float64
+    cost_value::Float64; cost_grad::Float64
 end
 struct OptResult                 # gprb_opt_result
     mll::Float64; g_norm::Float64
@@ -166,31 +212,37 @@ struct OptResult                 # gprb_opt_result
 end
 
 """
-    optimize!(gp_or_batch, method::Optim.LBFGS, options::Optim.Options; max_evals = 0)
+    GaussianProcesses.optimize!(gps::Vector{<:GPE}, method::Optim.LBFGS, options::Optim.Options; max_evals, cost_value, cost_grad)
 
-Same positional signature as the reference's `GaussianProcesses.optimize!(gp, LBFGS(linesearch=BackTracking(order=2)),
-Optim.Options(time_limit=10.))` (CPnoise.jl:41).  `options.time_limit` is wall-clock for the whole batch; `max_evals`
-is the deterministic stopping rule used for parity runs.
+Batched form of the reference's `GaussianProcesses.optimize!(gp, LBFGS(linesearch=BackTracking(order=2)),
+Optim.Options(time_limit=10.))` (CPnoise.jl:41): all GPs advance in lock-step inside ONE gprb_optimize call.
+`options.time_limit` is the reference's per-GP 10 s: with `cost_value` / `cost_grad` (seconds one value-only / value+gradient
+evaluation takes on the CPU being emulated) it runs on a deterministic per-GP virtual clock; without them it is the wall
+clock of the whole batch.  `max_evals` is a per-GP evaluation cap.
 """
-function optimize!(batch::GPBatch, method::Optim.LBFGS = Optim.LBFGS(), options::Optim.Options = Optim.Options(); max_evals::Integer = 0)
+function GaussianProcesses.optimize!(gps::Vector{<:GPE}, method::Optim.LBFGS = Optim.LBFGS(), options::Optim.Options = Optim.Options();
+                                     max_evals::Integer = 0, cost_value::Real = 0.0, cost_grad::Real = 0.0)
+    batch = (haskey(RESIDENT, gps[1]) && RESIDENT[gps[1]][1].gps == gps) ? RESIDENT[gps[1]][1] : GPBatch(gps)
     ls = method.linesearch!
     o = LbfgsOpts(method.m, options.iterations, max_evals, ls.iterations, options.g_abstol,
-                  isfinite(options.time_limit) ? options.time_limit : 0.0, ls.c_1, ls.ρ_hi, ls.ρ_lo)
+                  isfinite(options.time_limit) ? options.time_limit : 0.0, ls.c_1, ls.ρ_hi, ls.ρ_lo, cost_value, cost_grad)
     θ = thetas(batch)
     res = Vector{OptResult}(undef, batch.B)
     check(ccall((:gprb_optimize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{LbfgsOpts}, Ptr{OptResult}), batch.handle, θ, o, res))
     for (b, gp) in enumerate(batch.gps)
-        setparams!(gp, θ[:, b])
-        gp.mll, gp.info = res[b].mll, res[b].info
+        set_params!(gp, θ[:, b])
+        gp.mll = res[b].mll; gp.target = res[b].mll
     end
+    batch.cache_key = zeros(0, 0)
     res
 end
-optimize!(gp::GPE, args...; kw...) = optimize!(gp.batch !== nothing && gp.batch.B == 1 ? gp.batch : GPBatch([gp]), args...; kw...)[1]
-optimize!(gps::Vector{GPE}, args...; kw...) = optimize!(GPBatch(gps), args...; kw...)
+# the reference's per-GP call (CPnoise.jl:41) on a B200-resident GPE: a batch of one through the same driver
+GaussianProcesses.optimize!(gp::B200GPE, method::Optim.LBFGS = Optim.LBFGS(), options::Optim.Options = Optim.Options(); kw...) =
+    GaussianProcesses.optimize!(GPE[gp], method, options; kw...)[1]
 
 # ---- predict_y -------------------------------------------------------------------------------------------------------
-"predict_y(batch, Xstar::d×m) -> (μ::B×m... stored m×B, σ²) ; `var=false` skips the variance the reference discards."
-function predict_y(batch::GPBatch, Xstar::AbstractMatrix; var::Bool = true)
+"predict_y(batch, Xstar::d×m) -> (μ::m×B, σ²::m×B | nothing); `var=false` skips the variance the reference discards. GPs without state give NaN columns."
+function GaussianProcesses.predict_y(batch::GPBatch, Xstar::AbstractMatrix; var::Bool = true)
     Xs = Matrix{Float64}(Xstar)
     m = size(Xs, 2)
     mstar = nothing
@@ -208,9 +260,65 @@ function predict_y(batch::GPBatch, Xstar::AbstractMatrix; var::Bool = true)
     end
     μ, σ2
 end
-function predict_y(gp::GPE, Xstar::AbstractMatrix)                 # reference call pattern: (μ::Vector, σ²::Vector)
-    μ, σ2 = predict_y(gp.batch, Xstar)
-    μ[:, gp.slot], σ2[:, gp.slot]
+
+# The reference's call `predict_y(gp, obs)[1][1]` (predictdynamics.jl:13), once per GP of the trial with the SAME obs:
+# the first call predicts every GP of the batch on the device, the other G-1 calls are served from the step cache
+# (the device-side twin of MDCache, src/mDynamics.jl:6-11).
+function GaussianProcesses.predict_y(gp::B200GPE, Xstar::AbstractMatrix)
+    batch, slot = residence(gp)
+    if size(batch.cache_key) != size(Xstar) || batch.cache_key != Xstar
+        μ, σ2 = GaussianProcesses.predict_y(batch, Xstar; var = true)
+        batch.cache_key, batch.cache_mu, batch.cache_var = Matrix{Float64}(Xstar), μ, σ2
+    end
+    batch.cache_mu[:, slot], batch.cache_var[:, slot]
 end
+
+# ---- asynchronous rollout step (two trial groups alternate: device predict of one under the host projectv! of the other) -----
+"Enqueue the mean prediction of GPs gp0:gp1 (1-based, inclusive) at the per-trial state blocks `states` (d × m × trials) on pipeline `slot`."
+function predict_async!(batch::GPBatch, slot::Integer, gp0::Integer, gp1::Integer, states::Array{Float64,3}, G::Integer; var::Bool = false)
+    d, m, _ = size(states)
+    GC.@preserve states begin
+        check(ccall((:gprb_predict_async, LIB), Cint,
+                    (Ptr{Cvoid}, Int32, Int32, Int32, Int64, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Int32),
+                    batch.handle, slot, gp0 - 1, gp1, m, states, d * m, G, C_NULL, var ? 1 : 0))
+    end
+end
+function predict_wait!(batch::GPBatch, slot::Integer, count::Integer, m::Integer; var::Bool = false)
+    μ = Matrix{Float64}(undef, m, count)
+    σ2 = var ? Matrix{Float64}(undef, m, count) : nothing
+    check(ccall((:gprb_predict_wait, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}),
+                batch.handle, slot, μ, var ? pointer(σ2) : C_NULL))
+    μ, σ2
+end
+
+# ---- glue the experiment drivers need ---------------------------------------------------------------------------------
+"config.json order `[σ_f, ℓ_1..ℓ_d]` (examples/config/README) -> GaussianProcesses order `[logNoise, ll_1..ll_d, lσ]` (CPnoise.jl:38)."
+params_to_theta(params::AbstractVector; logNoise::Real = -2.0) = vcat(Float64(logNoise), log.(params[2:end]), log(params[1]))
+"Inverse of params_to_theta: what parallelsearch stores in `config[\"params\"]` / the JSON checkpoints (core.jl:94-112, utils.jl:48-63)."
+theta_to_params(θ::AbstractVector) = vcat(exp(θ[end]), exp.(θ[2:end-1]))
+
+"""
+    gather_results(local_rows::Dict{Int,Vector{Float64}}, ntrials, width) -> Matrix (width × ntrials)
+
+The final gather of per-trial results across ranks (replaces the lock-guarded result callbacks of core.jl:47-56 when the
+trials are sharded over GPUs): one ncclAllGather inside libgprb200.so.  Ranks join with `comm_init_rank!` (the 128-byte id
+from `comm_unique_id()` on rank 0 travels through Distributed.jl / MPI / a file).  Rows are `kstep_mse`, `projectionerror`,
+`params` ... in whatever layout `resultcallback!` needs; trial ids are 1-based here, 0-based in the C ABI.
+"""
+function gather_results(local_rows::Dict{Int,Vector{Float64}}, ntrials::Integer, width::Integer)
+    ids = Int32[t - 1 for t in sort(collect(keys(local_rows)))]
+    rows = isempty(ids) ? zeros(width, 0) : reduce(hcat, [local_rows[t + 1] for t in ids])     # width × count = row-major count × width
+    out = Matrix{Float64}(undef, width, ntrials)
+    check(ccall((:gprb_gather, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                context(), ntrials, width, length(ids), ids, rows, out))
+    out
+end
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:gprb_comm_unique_id, LIB), Cint, (Ptr{Cvoid},), id))
+    id
+end
+comm_init_rank!(nranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ccall((:gprb_comm_init_rank, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}), context(), nranks, rank, id))
 
 end # module

@@ -276,3 +276,34 @@ def test_optimize_per_gp_virtual_time_limit(gprb):
         assert res[k]["f_calls"] * 0.4 + res[k]["g_calls"] * 1.1 > 10.0          # stopped at the first iteration past 10 s
         assert abs(res[k]["minimum"] - o.f) <= 1e-6 * abs(o.f)
     batch.close()
+
+
+@pytest.mark.parametrize("system,n", [("CP", 300), ("P2", 1000), ("CP", 2000)])
+def test_cluster_substitution_is_bit_identical(gprb, system, n, monkeypatch):
+    """k_solve_cluster (one thread-block cluster of up to 8 CTAs per GP, used when a pass has fewer GPs than SMs) adds its
+    terms in exactly the order of the one-CTA k_solve: alpha, mll and everything downstream are bit-identical, so a GP's
+    results still do not depend on the batch it is evaluated in.  J = 3 (ragged last block), 8 and 16 block rows."""
+    from gpr_jl_b200 import data
+    tr = data.make_trial(system, n, seed=7 + n, n_test=5)
+    th = data.theta0(system, tr["X"])
+    th[1:-1] -= 0.5
+    G = min(3, tr["Y"].shape[0])
+    thetas = np.tile(th, (G, 1)) + 0.05 * np.random.default_rng(n).standard_normal((G, th.size))
+
+    def run(below):
+        monkeypatch.setenv("GPRB200_SOLVE_CLUSTER_BELOW", below)  # read when the batch is created
+        gps = [gprb.GPE(tr["X"], tr["Y"][k], gprb.MeanZero(), gprb.SEArd(thetas[k][1:-1], thetas[k][-1]), logNoise=thetas[k][0])
+               for k in range(G)]
+        b = gprb.GPBatch(gps)
+        mll, grad, info = b.eval(grad=True)
+        al = np.stack([b.alpha(k) for k in range(G)])
+        mu, var = b.predict_y(tr["Xtest"])
+        b.close()
+        return mll, grad, info, al, mu, var
+    one = run("0")
+    clu = run("100000")
+    for a, c in zip(one, clu):
+        assert np.array_equal(a, c)
+    X = np.ascontiguousarray(tr["X"].T)
+    r = go.eval_mll(X, tr["Y"][0], thetas[0], with_grad=True, return_state=True)
+    assert abs(clu[0][0] - r["mll"]) <= 1e-8 * abs(r["mll"]) and rel(clu[3][0], r["state"]["alpha"]) <= 1e-8

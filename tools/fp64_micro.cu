@@ -80,6 +80,16 @@ int main() {
     ms = time_ms([&] { dfma_kernel<1><<<sms, 128>>>(out, iters, 1.0000001, 1e-9); });
     printf(", \"dfma_dep_chain_ns\": %.2f", ms * 1e6 / iters);
   }
+  {  // how far does ONE warp per SMSP get with many independent accumulators? (half-tile GEMM CTAs have one consumer warp
+     // per SMSP: if a single warp cannot saturate the DMMA pipe, two co-resident CTAs cannot hide each other's idle phases)
+    for (int warps = 1; warps <= 4; warps *= 2) {
+      double ms = time_ms([&] { dmma_kernel<32><<<sms, 128 * warps>>>(out, iters / 8, 1.0000001, 1e-9); });
+      double tf = 2.0 * 256 * 32 * (iters / 8) * 4.0 * warps * sms / (ms * 1e-3) / 1e12;
+      printf(", \"dmma_tflops_%dwarp_per_smsp_32acc\": %.2f", warps, tf);
+    }
+    double ms = time_ms([&] { dmma_kernel<8><<<sms, 128>>>(out, iters / 2, 1.0000001, 1e-9); });
+    printf(", \"dmma_tflops_1warp_per_smsp_8acc\": %.2f", 2.0 * 256 * 8 * (iters / 2) * 4.0 * sms / (ms * 1e-3) / 1e12);
+  }
   printf("}\n");
   CK(cudaGetLastError());
   return 0;

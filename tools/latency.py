@@ -28,13 +28,14 @@ for system, B in (("CP", 1), ("CP", 4), ("FB", 12)):
             fn()
         return (time.perf_counter() - t0) / reps * 1e3
 
-    t_g = timeit(lambda: batch.eval(grad=True))
     t_v = timeit(lambda: batch.eval(grad=False))
     x1 = tr["Xtest"][:, :1]
-    t_p1 = timeit(lambda: batch.predict_y(x1, var=True))
+    t_p1 = timeit(lambda: batch.predict_y(x1, var=True))     # value-only state (after optimize!): blocked forward substitution
     t_pm = timeit(lambda: batch.predict_y(x1, var=False))
+    t_g = timeit(lambda: batch.eval(grad=True))
+    t_p1v = timeit(lambda: batch.predict_y(x1, var=True))    # V = L^-T resident (after a gradient evaluation): split GEMV path
     rows.append({"system": system, "B": B, "n": 2000, "d": tr["X"].shape[0], "eval_grad_ms": t_g, "eval_value_ms": t_v,
-                 "predict_1col_meanvar_ms": t_p1, "predict_1col_mean_ms": t_pm})
+                 "predict_1col_meanvar_ms": t_p1, "predict_1col_meanvar_Vresident_ms": t_p1v, "predict_1col_mean_ms": t_pm})
     print(json.dumps(rows[-1]), flush=True)
     batch.close()
     del batch

@@ -37,18 +37,21 @@ def main():
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle (one evaluation per point, n <= 2048)")
     ap.add_argument("--gb", type=float, default=8.0, help="target HBM footprint per point")
     ap.add_argument("--nmin", type=int, default=0, help="skip sizes below this n")
+    ap.add_argument("--nmax", type=int, default=1 << 30, help="skip sizes above this n")
+    ap.add_argument("--dims", default="13,26,39,52", help="comma-separated input dimensions")
+    ap.add_argument("--bmax", type=int, default=4096, help="cap on GPs per point (B is chosen to fill --gb of HBM)")
     a = ap.parse_args()
     import torch
     import gpr_jl_b200 as G
     peak = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAKS.json")))["dgemm_tflops_sustained"]
     dev = torch.device("cuda", 0)
-    ns = [n for n in [256, 512, 1024, 2048] + ([] if a.quick else [4096, 8192]) if n >= a.nmin]
+    ns = [n for n in [256, 512, 1024, 2048] + ([] if a.quick else [4096, 8192]) if a.nmin <= n <= a.nmax]
     rows = []
     for n in ns:
-        for d in (13, 26, 39, 52):
+        for d in [int(x) for x in a.dims.split(",")]:
             npad = (n + 127) // 128 * 128
             per_gp = 2 * npad * npad * 8 + 3 * npad * 128 * 8 + npad * 128 * 8
-            B = int(max(4, min(512, a.gb * 1e9 // per_gp)))
+            B = int(max(4, min(a.bmax, a.gb * 1e9 // per_gp)))
             G4 = 4  # GPs per dataset (like the 4 outputs of a CP trial)
             B = B // G4 * G4
             rng = np.random.default_rng(n * 100 + d)
@@ -85,10 +88,10 @@ def main():
             m = 100
             Xs = np.asfortranarray(rng.standard_normal((d, m)))
             batch.predict_y(Xs, var=True)
-            t0 = time.perf_counter()
-            for _ in range(2):
+            tp = 0.0
+            for _ in range(3):  # device time of gprb_predict (CUDA events on the library's stream, copies included)
                 batch.predict_y(Xs, var=True)
-            tp = (time.perf_counter() - t0) / 2
+                tp += batch.last_predict_ms(0) * 1e-3 / 3
             row = {"n": n, "d": d, "B": B, "info_ok": ok,
                    "evals_per_s": B / tg, "frac_fp64_peak": f_eval(n, d) * B / tg / 1e12 / peak,
                    "value_only_evals_per_s": B / tv, "value_only_frac_fp64_peak": f_value(n, d) * B / tv / 1e12 / peak,
