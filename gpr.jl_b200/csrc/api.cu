@@ -95,6 +95,10 @@ static void free_batch(gprb_batch* b) {
   }
   for (int s = 0; s < 8; ++s)
     if (b->ev[s]) cudaEventDestroy(b->ev[s]);
+  for (int s = 0; s < 4; ++s) {
+    if (b->la_fac[s]) cudaEventDestroy(b->la_fac[s]);
+    if (b->la_rest[s]) cudaEventDestroy(b->la_rest[s]);
+  }
   for (cudaEvent_t e : b->gemm_ev) cudaEventDestroy(e);
   delete b;
 }
@@ -104,7 +108,7 @@ static void free_batch(gprb_batch* b) {
 // the first `nreuse` (<= ngrad), whose factor, alpha and mll of the previous evaluation at the same theta are still
 // resident (the optimiser asks for the gradient at the point its line search just accepted).
 static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nreuse, bool right_looking, cudaStream_t st,
-                            bool prof) {
+                            bool prof, int group = -1) {
   if (count <= 0) return 0;
   const bool with_grad = ngrad > 0;
   const int32_t* glist = b->list + off;     // inverse + gradient: glist[0 .. ngrad)
@@ -172,8 +176,19 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   if (prof) cudaEventRecord(b->ev[1], st);
   DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
   if (right_looking) ga.Cin = b->Lm;  // S lives (and is updated in place) in the lower tiles of Lm
+  // One-column look-ahead (left-looking schedule, stream groups of a normal pass): the serial part of a block column -
+  // CHOL_DIAG(j) tile -> potf2/trtri of the diagonal block -> the ONE tile L(j+1, j) the next diagonal tile needs - stays
+  // on the group's stream; the other tiles of the column, L(j+2.., j), run on an auxiliary stream behind an event.
+  // So CHOL_DIAG(j+1) and its potf2 (one CTA or two per GP, mostly latency) execute UNDER the bulk of column j instead of
+  // after it.  Dependencies: COL_rest(j) needs Dinv_j (event `fac`) and the earlier COL_rest launches (aux-stream order);
+  // the first tile of column j needs row j+1 of COL_rest(j-1) (event `rest`); CHOL_DIAG(j+1) only reads L(j+1, <= j),
+  // all produced by then.  The arithmetic of every tile is unchanged.
+  const bool lookahead = !right_looking && !prof && group >= 0 && J >= 3 && b->lookahead && b->nstreams <= 4;
+  cudaStream_t aux = lookahead ? b->stream[4 + group] : nullptr;
+  if (lookahead) GPRB_CUDA(cudaStreamWaitEvent(aux, b->la_rest[group], 0));  // (no-op ordering anchor after an earlier pass)
   for (int j = 0; j < J; ++j) {
     ga.step = j;
+    ga.bx_off = 0;
     if (!right_looking) {
       ga.mode = GEMM_CHOL_DIAG;
       if ((rc = gemm(ga, 1))) return rc;
@@ -184,8 +199,22 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
     ++launches;
     if (j + 1 < J) {
       ga.mode = right_looking ? GEMM_CHOL_PANEL : GEMM_CHOL_COL;
-      if ((rc = gemm(ga, J - 1 - j))) return rc;
-      ++launches;
+      if (lookahead) {
+        GPRB_CUDA(cudaEventRecord(b->la_fac[group], st));
+        if (j > 0) GPRB_CUDA(cudaStreamWaitEvent(st, b->la_rest[group], 0));  // COL_rest(j-1) produced L(j+1, j-1)
+        if ((rc = launch_tile_gemm(ga, 1, count, st))) return rc;               // L(j+1, j)
+        ++launches;
+        if (J - 2 - j > 0) {
+          GPRB_CUDA(cudaStreamWaitEvent(aux, b->la_fac[group], 0));
+          ga.bx_off = 1;
+          if ((rc = launch_tile_gemm(ga, J - 2 - j, count, aux))) return rc;    // L(j+2 .., j)
+          ++launches;
+          GPRB_CUDA(cudaEventRecord(b->la_rest[group], aux));
+        }
+      } else {
+        if ((rc = gemm(ga, J - 1 - j))) return rc;
+        ++launches;
+      }
       if (right_looking) {
         ga.mode = GEMM_CHOL_TRAIL;
         if ((rc = gemm(ga, (J - 1 - j) * (J - j) / 2))) return rc;
@@ -193,6 +222,8 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
       }
     }
   }
+  ga.bx_off = 0;
+  if (lookahead) GPRB_CUDA(cudaStreamWaitEvent(st, b->la_rest[group], 0));  // the last COL_rest before the substitution
   if (prof) cudaEventRecord(b->ev[2], st);
   SolveArgs sa{b->Lm, b->Dinv, b->ymm, b->logdet_part, b->fail, b->zbuf, b->alpha, b->mll, list, ms, dstride,
                (int)b->n, (int)b->npad, J, nv};
@@ -281,7 +312,7 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
   for (size_t s = 0; s < groups.size(); ++s) {
     const Group& g = groups[s];
     if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(b->stream[s], b->join[0], 0));
-    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[s], false))) return rc;
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[s], false, s < 4 ? (int)s : -1))) return rc;
     if (s > 0) {
       GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
       GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
@@ -741,6 +772,8 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
     // cluster per GP; above that the one-CTA-per-GP kernel already streams at the HBM roof and clusters only add barriers
     // (measured: 100-GP groups, 122.0 -> 129.2 ms per 400-GP step with clusters)
     b->solve_cluster_below = ctx->sm_count / 4 + 1;
+    b->lookahead = true;
+    if (const char* ev = getenv("GPRB200_LOOKAHEAD")) b->lookahead = atoi(ev) != 0;
     if (const char* ev = getenv("GPRB200_SOLVE_CLUSTER_BELOW")) b->solve_cluster_below = atoi(ev);
     if (const char* ev = getenv("GPRB200_STREAMS")) b->nstreams = std::max(1, std::min(MAX_STREAMS, atoi(ev)));
     for (int s = 0; s < MAX_STREAMS && !rc; ++s) {
@@ -750,6 +783,10 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
     }
     for (int s = 0; s < 8 && !rc; ++s)
       if ((e = cudaEventCreate(&b->ev[s])) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
+    for (int s = 0; s < 4 && !rc; ++s)
+      if ((e = cudaEventCreateWithFlags(&b->la_fac[s], cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&b->la_rest[s], cudaEventDisableTiming)) != cudaSuccess)
+        rc = cuda_fail(e, "cudaEventCreate(look-ahead)", __FILE__, __LINE__);
     if (rc) break;
     std::vector<const double*> xp(B), xtp(B);
     for (int i = 0; i < B; ++i) { xp[i] = ds[i]->X; xtp[i] = ds[i]->Xt; }

@@ -214,14 +214,20 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
 // ---------------------------------------------------------------------------------------------
 constexpr int SOLVE_THREADS = 512;
 
-// rows rb, rb + 32, rb + 64, rb + 96 of one 128-row block of column Lcol against alpha (rows >= nv are padding)
-__device__ __forceinline__ void backward_block(const double* Lcol, const double* al, int rb, int nv, double& a0, double& a1) {
-  const double l0 = rb < nv ? Lcol[rb] : 0.0, l1 = rb + 32 < nv ? Lcol[rb + 32] : 0.0;
-  const double l2 = rb + 64 < nv ? Lcol[rb + 64] : 0.0, l3 = rb + 96 < nv ? Lcol[rb + 96] : 0.0;
-  if (rb < nv) a0 = fma(l0, al[rb], a0);
-  if (rb + 32 < nv) a1 = fma(l1, al[rb + 32], a1);
-  if (rb + 64 < nv) a0 = fma(l2, al[rb + 64], a0);
-  if (rb + 96 < nv) a1 = fma(l3, al[rb + 96], a1);
+// sum_{r >= rbeg} Lcol[r] alpha[r] over one column of L by one warp (lanes over rows, two accumulators, ascending rows,
+// shuffle tree): the summation order of the backward sweep, shared by k_solve and k_solve_cluster (bit-identical results).
+__device__ __forceinline__ double backward_column(const double* Lcol, const double* al, int rbeg, int nv, int lane) {
+  double a0 = 0.0, a1 = 0.0;
+  int r = rbeg + lane;
+  for (; r + 32 < nv; r += 64) {
+    a0 = fma(Lcol[r], al[r], a0);
+    a1 = fma(Lcol[r + 32], al[r + 32], a1);
+  }
+  for (; r < nv; r += 32) a0 = fma(Lcol[r], al[r], a0);
+  double s = a0 + a1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  return s;
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
@@ -270,23 +276,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
     __syncthreads();
   }
 
-  // ---- backward: alpha_j = Dinv_j^T (z_j - sum_{i>j} L(i,j)^T alpha_i); warp per column, lanes over rows.
-  // Canonical summation order (shared with k_solve_cluster, which receives alpha_i block by block from i = J-1 down):
-  // block rows i = J-1 .. jb+1, inside a block the lane's rows lane, +32, +64, +96 alternate between two accumulators.
+  // ---- backward: alpha_j = Dinv_j^T (z_j - sum_{i>j} L(i,j)^T alpha_i); warp per column, lanes over rows
   for (int jb = J - 1; jb >= 0; --jb) {
+    const int rbeg = (jb + 1) * NB;
     for (int c = warp; c < NB; c += SOLVE_THREADS / 32) {
       const double* Lcol = L + (int64_t)(jb * NB + c) * npad;
       double a0 = 0.0, a1 = 0.0;
-      if (J - 1 > jb) backward_block(Lcol, al, (J - 1) * NB + lane, nv, a0, a1);  // only the last block row is ragged
-#pragma unroll 4
-      for (int i = J - 2; i > jb; --i) {  // full blocks: eight and more independent loads in flight per lane
-        const int rb = i * NB + lane;
-        const double l0 = Lcol[rb], l1 = Lcol[rb + 32], l2 = Lcol[rb + 64], l3 = Lcol[rb + 96];
-        a0 = fma(l0, al[rb], a0);
-        a1 = fma(l1, al[rb + 32], a1);
-        a0 = fma(l2, al[rb + 64], a0);
-        a1 = fma(l3, al[rb + 96], a1);
+      int r = rbeg + lane;
+      for (; r + 32 < nv; r += 64) {  // (backward_column, written out: the order k_solve_cluster reproduces)
+        a0 = fma(Lcol[r], al[r], a0);
+        a1 = fma(Lcol[r + 32], al[r + 32], a1);
       }
+      for (; r < nv; r += 32) a0 = fma(Lcol[r], al[r], a0);
       double s = a0 + a1;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs g) {
 //   forward   block row i belongs to CTA i mod C; its thread (row, k-partition) keeps the four running sums of
 //             k_solve in registers and adds block column j when z_j arrives; the owner of block row j finishes z_j with
 //             the inverted diagonal block and writes it into every CTA's copy through distributed shared memory
-//   backward  block column j belongs to CTA j mod C; alpha_i arrives from i = J-1 down
+//   backward  the columns of block column j are dealt over the CTAs; the owner-less diagonal solve is replicated
 // Every thread adds its terms in exactly the order of k_solve, so both kernels give bit-identical results (a GP's
 // numbers do not depend on how many GPs share its pass - tests/test_gpu_parity.py::test_results_do_not_depend_...).
 // ---------------------------------------------------------------------------------------------------------
@@ -399,48 +400,28 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_cluster(SolveArgs g, in
     }
   }
 
-  // ---- backward
-  double ba[MAXOWN][NB / (SOLVE_THREADS / 32)][2];
-#pragma unroll
-  for (int o = 0; o < MAXOWN; ++o)
-#pragma unroll
-    for (int cc = 0; cc < NB / (SOLVE_THREADS / 32); ++cc) ba[o][cc][0] = ba[o][cc][1] = 0.0;
-  for (int i = J - 1; i >= 0; --i) {
-    if (q == i % C) {
-      const int o = i / C;
-#pragma unroll
-      for (int cc = 0; cc < NB / (SOLVE_THREADS / 32); ++cc) {
-        const int c = warp + cc * (SOLVE_THREADS / 32);
-        double s = 0.0;
-#pragma unroll
-        for (int oo = 0; oo < MAXOWN; ++oo)
-          if (oo == o) s = ba[oo][cc][0] + ba[oo][cc][1];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) rv[c] = z[i * NB + c] - s;
-      }
-      __syncthreads();
-      const double* Dj = Dinv + (int64_t)i * NB * NB;
-      for (int c = warp; c < NB; c += SOLVE_THREADS / 32) {
-        double s = 0.0;
-        for (int kk = c + lane; kk < NB; kk += 32) s = fma(Dj[kk + c * NB], rv[kk], s);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane < C) cluster.map_shared_rank(al, lane)[i * NB + c] = s;  // lane r writes CTA r's copy
-      }
+  // ---- backward: the 128 columns of block column jb are dealt over the CTAs (column c -> CTA c mod C); a warp sums its
+  // column over ALL rows below the block in k_solve's order, the differences z - sum go to every CTA's copy (double
+  // buffered: a CTA can be one step ahead of the slowest), and every CTA finishes alpha_jb with the inverted diagonal
+  // block for itself - one cluster barrier per block column
+  for (int jb = J - 1; jb >= 0; --jb) {
+    double* rvb = (jb & 1) ? red : rv;
+    const int rbeg = (jb + 1) * NB;
+    for (int c = q + C * warp; c < NB; c += C * (SOLVE_THREADS / 32)) {
+      const double s = backward_column(L + (int64_t)(jb * NB + c) * npad, al, rbeg, nv, lane);
+      const double v = z[jb * NB + c] - s;
+      if (lane < C) cluster.map_shared_rank(rvb, lane)[c] = v;  // lane r writes CTA r's copy
     }
     cluster.sync();
+    const double* Dj = Dinv + (int64_t)jb * NB * NB;
+    for (int c = warp; c < NB; c += SOLVE_THREADS / 32) {
+      double s = 0.0;
+      for (int kk = c + lane; kk < NB; kk += 32) s = fma(Dj[kk + c * NB], rvb[kk], s);
 #pragma unroll
-    for (int o = 0; o < MAXOWN; ++o) {
-      const int j = q + o * C;
-      if (j < J && j < i) {
-#pragma unroll
-        for (int cc = 0; cc < NB / (SOLVE_THREADS / 32); ++cc) {
-          const int c = warp + cc * (SOLVE_THREADS / 32);
-          backward_block(L + (int64_t)(j * NB + c) * npad, al, i * NB + lane, nv, ba[o][cc][0], ba[o][cc][1]);
-        }
-      }
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) al[jb * NB + c] = s;
     }
+    __syncthreads();
   }
 
   if (q != 0) return;

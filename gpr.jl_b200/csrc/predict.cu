@@ -48,7 +48,7 @@ __device__ __forceinline__ int chunk_begin(int i, int n) {
 // instead of one, and the result is bit-identical for every rsplit (i.e. for every batch size).
 template <int KIND, int PS>
 __global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ks = reinterpret_cast<double*>(smem_raw);  // [PS][npad]
   double* xs = ks + (size_t)PS * g.npad;              // [PS][MAX_D]
   double* w = xs + PS * MAX_D;                        // [MAX_D]

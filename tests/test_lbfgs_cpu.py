@@ -102,3 +102,32 @@ def test_start_at_optimum_and_nonfinite_start():
     assert res[0].iterations == 0 and res[0].converged == 1
     th, res = _run_lib(np.full((1, 3), 5.0), 2.0)  # outside the box: objective is +Inf at the start
     assert res[0].iterations == 0 and res[0].converged == 0
+
+
+def test_per_gp_virtual_time_limit_matches_oracle():
+    """time_limit with evaluation costs set runs on a deterministic per-GP virtual clock (the reference's
+    Optim.Options(time_limit=10.) is 10 s of CPU time per GP, CPnoise.jl:41): every GP stops at the first iteration
+    boundary where its own f_calls * cost_value + fg_calls * cost_grad exceeds the limit - GPs whose line searches
+    backtrack more stop after fewer iterations, exactly like the scalar restatement."""
+    rng = np.random.default_rng(11)
+    x0 = rng.uniform(-2, 2, (12, 5))
+    th, res = _run_lib(x0, 1e9, time_limit=10.0, cost_value=0.35, cost_grad=0.9)
+    f, fg = _f(1e9)
+    its = set()
+    for b in range(12):
+        r = lbfgs(f, fg, x0[b], LBFGSOptions(time_limit=10.0, cost_value=0.35, cost_grad=0.9))
+        assert r.stopped_by == "time_limit"
+        assert (res[b].iterations, res[b].f_calls, res[b].fg_calls) == (r.iterations, r.f_calls, r.fg_calls)
+        assert res[b].f_calls * 0.35 + res[b].fg_calls * 0.9 > 10.0
+        np.testing.assert_allclose(th[b], r.x, rtol=1e-12, atol=1e-12)
+        its.add((res[b].iterations, res[b].f_calls))
+    assert len(its) > 1  # the limit really is per GP: different GPs stop after different amounts of work
+
+
+def test_gradient_inf_norm_propagates_nan():
+    """maximum(abs, g) is NaN when any entry is NaN (Julia semantics): a failed gradient never counts as converged
+    (fmax dropped the NaN and reported ||g|| = 0)."""
+    # start inside the box but with the first step leaving it: the objective returns +Inf / NaN gradient outside
+    th, res = _run_lib(np.array([[1.9, 1.9, 1.9]]), 2.0, iterations=3)
+    assert np.all(np.isfinite(th)) and np.all(np.abs(th) <= 2.0)  # the optimiser never keeps a point outside the box
+    assert np.isfinite(res[0].mll)
