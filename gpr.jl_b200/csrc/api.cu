@@ -95,10 +95,6 @@ static void free_batch(gprb_batch* b) {
   }
   for (int s = 0; s < 8; ++s)
     if (b->ev[s]) cudaEventDestroy(b->ev[s]);
-  for (int s = 0; s < 4; ++s) {
-    if (b->la_fac[s]) cudaEventDestroy(b->la_fac[s]);
-    if (b->la_rest[s]) cudaEventDestroy(b->la_rest[s]);
-  }
   for (cudaEvent_t e : b->gemm_ev) cudaEventDestroy(e);
   delete b;
 }
@@ -108,7 +104,7 @@ static void free_batch(gprb_batch* b) {
 // the first `nreuse` (<= ngrad), whose factor, alpha and mll of the previous evaluation at the same theta are still
 // resident (the optimiser asks for the gradient at the point its line search just accepted).
 static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nreuse, bool right_looking, cudaStream_t st,
-                            bool prof, int group = -1) {
+                            bool prof) {
   if (count <= 0) return 0;
   const bool with_grad = ngrad > 0;
   const int32_t* glist = b->list + off;     // inverse + gradient: glist[0 .. ngrad)
@@ -174,47 +170,23 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   if ((rc = launch_assemble(aa, count, st))) return rc;
   ++launches;
   if (prof) cudaEventRecord(b->ev[1], st);
-  DiagArgs da{b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
+  DiagArgs da{nullptr, b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
   if (right_looking) ga.Cin = b->Lm;  // S lives (and is updated in place) in the lower tiles of Lm
-  // One-column look-ahead (left-looking schedule, stream groups of a normal pass): the serial part of a block column -
-  // CHOL_DIAG(j) tile -> potf2/trtri of the diagonal block -> the ONE tile L(j+1, j) the next diagonal tile needs - stays
-  // on the group's stream; the other tiles of the column, L(j+2.., j), run on an auxiliary stream behind an event.
-  // So CHOL_DIAG(j+1) and its potf2 (one CTA or two per GP, mostly latency) execute UNDER the bulk of column j instead of
-  // after it.  Dependencies: COL_rest(j) needs Dinv_j (event `fac`) and the earlier COL_rest launches (aux-stream order);
-  // the first tile of column j needs row j+1 of COL_rest(j-1) (event `rest`); CHOL_DIAG(j+1) only reads L(j+1, <= j),
-  // all produced by then.  The arithmetic of every tile is unchanged.
-  const bool lookahead = !right_looking && !prof && group >= 0 && J >= 3 && b->lookahead && b->nstreams <= 4;
-  cudaStream_t aux = lookahead ? b->stream[4 + group] : nullptr;
-  if (lookahead) GPRB_CUDA(cudaStreamWaitEvent(aux, b->la_rest[group], 0));  // (no-op ordering anchor after an earlier pass)
   for (int j = 0; j < J; ++j) {
     ga.step = j;
-    ga.bx_off = 0;
-    if (!right_looking) {
+    if (!right_looking && j > 0) {  // S(0,0) = K(0,0): k_diag_factor reads block column 0 straight from A
       ga.mode = GEMM_CHOL_DIAG;
       if ((rc = gemm(ga, 1))) return rc;
       ++launches;
     }
     da.step = j;
+    da.Src = (!right_looking && j == 0) ? b->A : nullptr;
     if ((rc = launch_diag_factor(da, count, st))) return rc;
     ++launches;
     if (j + 1 < J) {
       ga.mode = right_looking ? GEMM_CHOL_PANEL : GEMM_CHOL_COL;
-      if (lookahead) {
-        GPRB_CUDA(cudaEventRecord(b->la_fac[group], st));
-        if (j > 0) GPRB_CUDA(cudaStreamWaitEvent(st, b->la_rest[group], 0));  // COL_rest(j-1) produced L(j+1, j-1)
-        if ((rc = launch_tile_gemm(ga, 1, count, st))) return rc;               // L(j+1, j)
-        ++launches;
-        if (J - 2 - j > 0) {
-          GPRB_CUDA(cudaStreamWaitEvent(aux, b->la_fac[group], 0));
-          ga.bx_off = 1;
-          if ((rc = launch_tile_gemm(ga, J - 2 - j, count, aux))) return rc;    // L(j+2 .., j)
-          ++launches;
-          GPRB_CUDA(cudaEventRecord(b->la_rest[group], aux));
-        }
-      } else {
-        if ((rc = gemm(ga, J - 1 - j))) return rc;
-        ++launches;
-      }
+      if ((rc = gemm(ga, J - 1 - j))) return rc;
+      ++launches;
       if (right_looking) {
         ga.mode = GEMM_CHOL_TRAIL;
         if ((rc = gemm(ga, (J - 1 - j) * (J - j) / 2))) return rc;
@@ -222,8 +194,6 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
       }
     }
   }
-  ga.bx_off = 0;
-  if (lookahead) GPRB_CUDA(cudaStreamWaitEvent(st, b->la_rest[group], 0));  // the last COL_rest before the substitution
   if (prof) cudaEventRecord(b->ev[2], st);
   SolveArgs sa{b->Lm, b->Dinv, b->ymm, b->logdet_part, b->fail, b->zbuf, b->alpha, b->mll, list, ms, dstride,
                (int)b->n, (int)b->npad, J, nv};
@@ -266,10 +236,16 @@ static std::vector<Group> build_groups(gprb_batch* b, const std::vector<int32_t>
   const int S = (b->profiling || total < 8 || total <= b->rl_max || b->nstreams == 1) ? 1 : b->nstreams;
   std::vector<Group> groups;
   int off = 0;
+  // Unequal group sizes (weights 1 + skew, ..., 1 - skew): equal groups start together and run the same launches, so
+  // they reach their low-occupancy phases (diagonal tiles, potf2, the first rows of the triangular inverse) at the same
+  // time; groups of different size drift apart, and the thin phases of one fall under the wide phases of another.
+  std::vector<double> cum(S + 1, 0.0);
+  for (int s = 0; s < S; ++s) cum[s + 1] = cum[s] + (S > 1 ? 1.0 + b->group_skew * (double)(S - 1 - 2 * s) / (double)(S - 1) : 1.0);
+  auto cut = [&](size_t m, int s) { return (int)llround((double)m * cum[s] / cum[S]); };
   for (int s = 0; s < S; ++s) {
-    const int r0 = (int)((int64_t)reuse_gps.size() * s / S), r1 = (int)((int64_t)reuse_gps.size() * (s + 1) / S);
-    const int g0 = (int)((int64_t)grad_gps.size() * s / S), g1 = (int)((int64_t)grad_gps.size() * (s + 1) / S);
-    const int v0 = (int)((int64_t)val_gps.size() * s / S), v1 = (int)((int64_t)val_gps.size() * (s + 1) / S);
+    const int r0 = cut(reuse_gps.size(), s), r1 = cut(reuse_gps.size(), s + 1);
+    const int g0 = cut(grad_gps.size(), s), g1 = cut(grad_gps.size(), s + 1);
+    const int v0 = cut(val_gps.size(), s), v1 = cut(val_gps.size(), s + 1);
     Group g{off, (r1 - r0) + (g1 - g0) + (v1 - v0), (r1 - r0) + (g1 - g0), r1 - r0, !b->profiling && total <= b->rl_max};
     for (int k = r0; k < r1; ++k) b->list_host[off++] = reuse_gps[k];
     for (int k = g0; k < g1; ++k) b->list_host[off++] = grad_gps[k];
@@ -312,7 +288,7 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
   for (size_t s = 0; s < groups.size(); ++s) {
     const Group& g = groups[s];
     if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(b->stream[s], b->join[0], 0));
-    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[s], false, s < 4 ? (int)s : -1))) return rc;
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[s], false))) return rc;
     if (s > 0) {
       GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
       GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
@@ -772,8 +748,8 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
     // cluster per GP; above that the one-CTA-per-GP kernel already streams at the HBM roof and clusters only add barriers
     // (measured: 100-GP groups, 122.0 -> 129.2 ms per 400-GP step with clusters)
     b->solve_cluster_below = ctx->sm_count / 4 + 1;
-    b->lookahead = true;
-    if (const char* ev = getenv("GPRB200_LOOKAHEAD")) b->lookahead = atoi(ev) != 0;
+    b->group_skew = 0.0;
+    if (const char* ev = getenv("GPRB200_GROUP_SKEW")) b->group_skew = std::max(0.0, std::min(0.9, atof(ev)));
     if (const char* ev = getenv("GPRB200_SOLVE_CLUSTER_BELOW")) b->solve_cluster_below = atoi(ev);
     if (const char* ev = getenv("GPRB200_STREAMS")) b->nstreams = std::max(1, std::min(MAX_STREAMS, atoi(ev)));
     for (int s = 0; s < MAX_STREAMS && !rc; ++s) {
@@ -783,10 +759,6 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
     }
     for (int s = 0; s < 8 && !rc; ++s)
       if ((e = cudaEventCreate(&b->ev[s])) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
-    for (int s = 0; s < 4 && !rc; ++s)
-      if ((e = cudaEventCreateWithFlags(&b->la_fac[s], cudaEventDisableTiming)) != cudaSuccess ||
-          (e = cudaEventCreateWithFlags(&b->la_rest[s], cudaEventDisableTiming)) != cudaSuccess)
-        rc = cuda_fail(e, "cudaEventCreate(look-ahead)", __FILE__, __LINE__);
     if (rc) break;
     std::vector<const double*> xp(B), xtp(B);
     for (int i = 0; i < B; ++i) { xp[i] = ds[i]->X; xtp[i] = ds[i]->Xt; }

@@ -156,11 +156,10 @@ struct gprb_batch {
   cudaStream_t stream[gprb::MAX_STREAMS] = {};
   int nstreams = 1;
   int rl_max = 24;                // passes with at most this many GPs use the right-looking (low-latency) factorisation
+  double group_skew = 0.0;        // stream groups of a pass get sizes proportional to 1 + skew .. 1 - skew (GPRB200_GROUP_SKEW)
   int solve_cluster_below = 0;    // passes with fewer GPs than this use k_solve_cluster (GPRB200_SOLVE_CLUSTER_BELOW, default SM count)
   cudaEvent_t ev[8] = {};
   cudaEvent_t join[gprb::MAX_STREAMS] = {};
-  cudaEvent_t la_fac[4] = {}, la_rest[4] = {};  // one-column look-ahead of the Cholesky stage (group s: streams s and 4 + s)
-  bool lookahead = true;          // GPRB200_LOOKAHEAD=0 disables it (A/B comparisons)
   bool profiling = false;
   std::vector<uint8_t> state_ok;  // per GP: factor + alpha resident (last evaluation succeeded)
   std::vector<uint8_t> inv_ok;    // per GP: K^-1 resident in A (last evaluation was value+gradient)

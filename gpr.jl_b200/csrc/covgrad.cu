@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) k_assemble(AssembleArgs g) {
 constexpr int GA_THREADS = 256;
 constexpr int GA_CW = 64;             // columns per CTA
 constexpr int GA_LDJ = GA_CW + 4;     // padded row of the column-input tile (conflict-free B fragments)
+constexpr int GA_LDC = NB + 2;        // column stride of the cross-term tile: the accumulator stores of a half-warp hit
+                                      // (2 t) GA_LDC + g, distinct modulo 16 only for a stride = 2 mod 8 (132 gave 2-way conflicts)
 constexpr double GRAM_SMAX = 16.0;    // (d/4 + 2) eps * 16 < 4e-14 for d <= 62
 // Pairs whose kernel value underflows to zero are exact zeros either way and skip the exact path.  SEArd: exp(-r2/2)
 // underflows beyond r2 = 1500.  Matern: k ~ exp(-c r) with c = 1, sqrt 3, sqrt 5 only underflows beyond r = 750 / c.
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(GA_THREADS, CTAS) k_assemble_gram(AssembleArgs
   const int d = g.d, dpad = (d + 3) & ~3;
   double* Zi = reinterpret_cast<double*>(smem_raw);   // [dpad][LDS_T]  row-input tile, one padded row per dimension
   double* Zj = Zi + dpad * LDS_T;                      // [dpad][GA_LDJ] column-input tile
-  const int zreg = max(dpad * (LDS_T + GA_LDJ), GA_CW * LDS_T);  // the input tiles' space later holds the cross-term tile
+  const int zreg = max(dpad * (LDS_T + GA_LDJ), GA_CW * GA_LDC);  // the input tiles' space later holds the cross-term tile
   double* w = Zi + zreg;                               // [MAX_D + 2]  w_p
   double* sw = w + MAX_D + 2;                          // [MAX_D + 2]  sqrt(w_p)
   double* x0 = sw + MAX_D + 2;                         // [MAX_D + 2]  centre: first sample of the dataset
@@ -269,14 +271,14 @@ __global__ void __launch_bounds__(GA_THREADS, CTAS) k_assemble_gram(AssembleArgs
       for (int ni_ = 0; ni_ < 4; ++ni_) dmma884(acc[mi][ni_][0], acc[mi][ni_][1], a[mi], b[ni_]);
   }
   __syncthreads();  // norms visible; every warp is done with the input tiles: their space becomes the cross-term tile
-  double* Cs = Zi;  // [GA_CW][LDS_T] column-major z_i.z_j
+  double* Cs = Zi;  // [GA_CW][GA_LDC] column-major z_i.z_j
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni_ = 0; ni_ < 4; ++ni_) {
       const int rl = wm * 32 + mi * 8 + gq, cl = wn * 32 + ni_ * 8 + 2 * t;
-      Cs[cl * LDS_T + rl] = acc[mi][ni_][0];
-      Cs[(cl + 1) * LDS_T + rl] = acc[mi][ni_][1];
+      Cs[cl * GA_LDC + rl] = acc[mi][ni_][0];
+      Cs[(cl + 1) * GA_LDC + rl] = acc[mi][ni_][1];
     }
   __syncthreads();
   // epilogue, rolled (a fully unrolled register epilogue is instruction-fetch bound): thread = (row, 32-column half);
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(GA_THREADS, CTAS) k_assemble_gram(AssembleArgs
   for (int cl = cbeg; cl < cbeg + GA_CW / 2; ++cl) {
     const int c = c0 + cl;
     const double ssum = nr + nj[cl];
-    double r2 = fmax(ssum - 2.0 * Cs[cl * LDS_T + rl], 0.0);
+    double r2 = fmax(ssum - 2.0 * Cs[cl * GA_LDC + rl], 0.0);
     if (ssum > GRAM_SMAX && r2 - 4e-15 * ssum < gram_r2cut<KIND>() && rr < n && c < n) {  // exact path: direct differences of the raw inputs
       r2 = 0.0;
       for (int p = 0; p < d; ++p) {
@@ -604,7 +606,7 @@ int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream) {
   int rc = 0;
   if (!direct) {
     const int dpad = (a.d + 3) & ~3;
-    const size_t zreg = std::max((size_t)dpad * (LDS_T + GA_LDJ), (size_t)GA_CW * LDS_T);  // input tiles, later the cross-term tile
+    const size_t zreg = std::max((size_t)dpad * (LDS_T + GA_LDJ), (size_t)GA_CW * GA_LDC);  // input tiles, later the cross-term tile
     const size_t smem = (zreg + 3 * (MAX_D + 2) + NB + GA_CW) * sizeof(double) + 16;
     dim3 grid(a.J * (a.J + 1) / 2 * (NB / GA_CW), count);
     const bool three = 3 * (smem + 1024) <= 227 * 1024;  // three CTAs per SM fit (1 KB per CTA is reserved by the driver)

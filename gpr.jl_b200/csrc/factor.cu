@@ -53,11 +53,12 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
   const int64_t npad = g.npad;
   if (g.fail[gp] != 0) return;  // already failed (or non-finite theta): results are discarded by the host
   double* T = g.Lm + (int64_t)gp * g.mat_stride + (int64_t)j * NB + (int64_t)j * NB * npad;
+  const double* Tsrc = g.Src ? g.Src + (int64_t)gp * g.mat_stride + (int64_t)j * NB + (int64_t)j * NB * npad : T;
   // rows / cols beyond nv are padding the GEMM stages neither compute nor read: treat them as the identity here
   const int nvl = (j == g.J - 1) ? g.nv - j * NB : NB;
   for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
     const int r = idx & (NB - 1), c = idx >> 7;
-    S[c * LDS_T + r] = (r < nvl && c < nvl) ? T[r + c * npad] : (r == c ? 1.0 : 0.0);
+    S[c * LDS_T + r] = (r < nvl && c < nvl) ? Tsrc[r + c * npad] : (r == c ? 1.0 : 0.0);
   }
   if (tid == 0) bad_col = 0;
   __syncthreads();

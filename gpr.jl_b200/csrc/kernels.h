@@ -28,7 +28,6 @@ struct GemmArgs {
   int ncols = 128;      // valid test columns of the block (< 128: compact warp layout skips the padding columns)
   int colw = 64;        // columns per FWD_ROW tile (64 or 32): tile bx owns columns bx*colw .. of the block
   int gp_off = 0;       // first GP of this launch when `list` is null (stream groups of gprb_predict)
-  int bx_off = 0;       // CHOL_COL: first tile of the launch (tile = bx_off + blockIdx.x / 2): the look-ahead splits a column in two launches
   int t_gp_off = 0;     // GEMM_FWD_ROW: Tm is indexed by gp - t_gp_off (the right-hand-side blocks of a GP range start at its first GP)
   const int32_t* fail = nullptr;     // [B] per-GP failure flag: tiles of a GP whose factorisation already broke down exit at once
   unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)
@@ -55,6 +54,8 @@ int launch_assemble(const AssembleArgs& a, int count, cudaStream_t stream);
 
 // potf2 + trtri of the 128x128 diagonal block `step` (in place in Lm), emits Dinv, DinvT, logdet partials, fail flag.
 struct DiagArgs {
+  const double* Src = nullptr;  // where the block to factorise is read from (nullptr = Lm): block column 0 has no update
+                                // terms, so its diagonal block is taken straight from K (no CHOL_DIAG copy launch)
   double* Lm;
   double* Dinv;
   double* DinvT;

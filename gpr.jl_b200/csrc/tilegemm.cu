@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_tile_gemm(const __grid_cons
   const bool fwd = g.mode == GEMM_FWD_ROW;
   // blockIdx.x: (tile, half) for every mode but FWD_ROW, whose tiles are already <= 64 columns wide
   const int half = fwd ? 0 : (int)(blockIdx.x & 1);
-  const TileCoord tc = tile_coord(g.mode, g.step, g.J, fwd ? (int)blockIdx.x : g.bx_off + (int)(blockIdx.x >> 1));
+  const TileCoord tc = tile_coord(g.mode, g.step, g.J, fwd ? (int)blockIdx.x : (int)(blockIdx.x >> 1));
   HalfGeom hg;
   hg.r0h = COLSPLIT ? 0 : half * HB;
   hg.c0h = COLSPLIT ? (fwd ? 0 : half * HB) : 0;

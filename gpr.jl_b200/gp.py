@@ -625,7 +625,8 @@ class GPBatch:
         J = (self.n + 127) // 128
         labels = []
         for j in range(J):
-            labels.append(("chol_diag", j))
+            if j > 0:  # block column 0 has no update terms: its diagonal block is factorised straight from K
+                labels.append(("chol_diag", j))
             if j + 1 < J:
                 labels.append(("chol_col", j))
         labels += [("trtri_row", i) for i in range(1, J)] + [("lauum", 0)]

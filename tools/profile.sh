@@ -5,7 +5,7 @@
 #   3. full capture of one launch of each other kernel                              -> gpurun_out/<tag>_k<i>.ncu-rep
 # Usage: tools/profile.sh <tag>
 set -uo pipefail
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --trials 12 --cpu-seconds 0"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
@@ -16,7 +16,7 @@ $FULL > gpurun_out/${TAG}_full_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_B400.csv $FULL > gpurun_out/${TAG}_full_ncu.log 2>&1
 echo "full launch list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_tile_gemm -s 44 -c 3 -f -o gpurun_out/${TAG}_gemm $CMD > gpurun_out/${TAG}_ncu_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_tile_gemm -s 43 -c 3 -f -o gpurun_out/${TAG}_gemm $CMD > gpurun_out/${TAG}_ncu_gemm.log 2>&1
 echo "gemm capture rc=$?"
 i=0
 for K in k_grad_tiles k_assemble k_diag_factor k_solve k_predict_cross k_predict_finish; do

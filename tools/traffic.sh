@@ -3,7 +3,7 @@
 # ncu dram__bytes_{read,write}.sum of every k_tile_gemm launch; tools/traffic_parse.py keeps the 47 launches of the
 # final profiled evaluation (B = 400 GPs per launch) and writes profiles/<tag>_traffic.json.
 set -uo pipefail
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --no-predict --cpu-seconds 0"
 $CMD > gpurun_out/${TAG}_traffic_plain.log 2>&1 &&
