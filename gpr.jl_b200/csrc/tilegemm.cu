@@ -56,8 +56,10 @@ constexpr int NSTAGE = 3;
 constexpr int STAGE_DOUBLES = KT * (LDS_T + LDS_H);      // A + B operand chunk (one is 128 wide, the other 64)
 constexpr int RBUF_DOUBLES = KT * LDS_T;                 // one chunk of the post-multiplier (always 128 wide)
 constexpr int NRBUF = 2;                                 // ring depth of the post-multiplier chunks
-constexpr int N_CONSUMER_WARPS = 4;
-constexpr int GEMM_THREADS = (N_CONSUMER_WARPS + 4) * 32;  // the consumer warpgroup + the producer's warpgroup
+constexpr int N_CONSUMER_WARPS = 8;
+constexpr int MI_N = 4;                                  // 8-row slabs of a warp tile: 32 x 32 register tiles
+constexpr int WROWS = MI_N * 8;                          // rows of a warp tile
+constexpr int GEMM_THREADS = N_CONSUMER_WARPS * 32;      // no producer warp: warp 0 issues the (two) TMA requests of a chunk
 static_assert(2 * NSTAGE + 2 * NRBUF <= 16, "barrier block holds 16 mbarriers");
 static_assert(NSTAGE * STAGE_DOUBLES >= NB * LDS_H, "the parked half tile must fit the stage ring");
 constexpr size_t GEMM_SMEM = (size_t)(NSTAGE * STAGE_DOUBLES + NRBUF * RBUF_DOUBLES) * sizeof(double) + 16 * sizeof(uint64_t);
@@ -109,24 +111,23 @@ __device__ __forceinline__ TileCoord tile_coord(int mode, int step, int J, int b
   return tc;
 }
 
-enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_MI4, SEL_MI6, SEL_NI1, SEL_NI2, SEL_NI3, SEL_TRI0, SEL_TRI4,
-       SEL_MLO2, SEL_MLO4, SEL_MLO6, SEL_MLO2_NI3, SEL_MLO4_NI3, SEL_MLO6_NI3, SEL_NLO2 };
+enum { SEL_FULL = 0, SEL_SKIP, SEL_MI2, SEL_NI1, SEL_NI2, SEL_NI3, SEL_TRI0, SEL_MLO2, SEL_MLO2_NI3, SEL_NLO2 };
 
 // One k-chunk (KT = 16) of a warp's 64x32 register tile restricted, at compile time, to the 8x8 blocks
 // (mi, ni) with MI_LO <= mi < MI_LIM, NI_LO <= ni < NI_LIM and mi >= ni + OFF: straight-line unpredicated DMMAs.
 // LDA / LDB: smem row strides of the two k-major operand chunks.
 template <int LDA, int LDB, int MI_LIM, int NI_LIM, int OFF, int MI_LO = 0, int NI_LO = 0>
-__device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* ap, const double* bp) {
+__device__ __forceinline__ void chunk_mma(double (&acc)[MI_N][4][2], const double* ap, const double* bp) {
   // ap / bp: this lane's fragment pointers at k4 = 0, i.e. base + t * LD + row0 (resp. col0)
 #pragma unroll
   for (int k4 = 0; k4 < KT / 4; ++k4, ap += 4 * LDA, bp += 4 * LDB) {
-    double a[8], b[4];
+    double a[MI_N], b[4];
 #pragma unroll
     for (int mi = MI_LO; mi < MI_LIM; ++mi)
       if (mi >= OFF) a[mi] = ap[mi * 8];
 #pragma unroll
     for (int ni = NI_LO; ni < NI_LIM; ++ni)
-      if (ni + OFF <= 7) b[ni] = bp[ni * 8];
+      if (ni + OFF <= MI_N - 1) b[ni] = bp[ni * 8];
 #pragma unroll
     for (int mi = MI_LO; mi < MI_LIM; ++mi)
 #pragma unroll
@@ -137,25 +138,18 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[8][4][2], const double* 
 
 // Dispatch one chunk to the specialised body `sel` (warp-uniform).
 template <int LDA, int LDB>
-__device__ __forceinline__ void chunk_dispatch(int sel, double (&acc)[8][4][2], const double* ap, const double* bp) {
+__device__ __forceinline__ void chunk_dispatch(int sel, double (&acc)[MI_N][4][2], const double* ap, const double* bp) {
   switch (sel) {
     case SEL_SKIP: break;
     case SEL_MI2: chunk_mma<LDA, LDB, 2, 4, -64>(acc, ap, bp); break;
-    case SEL_MI4: chunk_mma<LDA, LDB, 4, 4, -64>(acc, ap, bp); break;
-    case SEL_MI6: chunk_mma<LDA, LDB, 6, 4, -64>(acc, ap, bp); break;
-    case SEL_NI1: chunk_mma<LDA, LDB, 8, 1, -64>(acc, ap, bp); break;
-    case SEL_NI2: chunk_mma<LDA, LDB, 8, 2, -64>(acc, ap, bp); break;
-    case SEL_NI3: chunk_mma<LDA, LDB, 8, 3, -64>(acc, ap, bp); break;
-    case SEL_TRI0: chunk_mma<LDA, LDB, 8, 4, 0>(acc, ap, bp); break;
-    case SEL_TRI4: chunk_mma<LDA, LDB, 8, 4, 4>(acc, ap, bp); break;
-    case SEL_MLO2: chunk_mma<LDA, LDB, 8, 4, -64, 2>(acc, ap, bp); break;
-    case SEL_MLO4: chunk_mma<LDA, LDB, 8, 4, -64, 4>(acc, ap, bp); break;
-    case SEL_MLO6: chunk_mma<LDA, LDB, 8, 4, -64, 6>(acc, ap, bp); break;
-    case SEL_MLO2_NI3: chunk_mma<LDA, LDB, 8, 3, -64, 2>(acc, ap, bp); break;
-    case SEL_MLO4_NI3: chunk_mma<LDA, LDB, 8, 3, -64, 4>(acc, ap, bp); break;
-    case SEL_MLO6_NI3: chunk_mma<LDA, LDB, 8, 3, -64, 6>(acc, ap, bp); break;
-    case SEL_NLO2: chunk_mma<LDA, LDB, 8, 4, -64, 0, 2>(acc, ap, bp); break;
-    default: chunk_mma<LDA, LDB, 8, 4, -64>(acc, ap, bp); break;
+    case SEL_NI1: chunk_mma<LDA, LDB, MI_N, 1, -64>(acc, ap, bp); break;
+    case SEL_NI2: chunk_mma<LDA, LDB, MI_N, 2, -64>(acc, ap, bp); break;
+    case SEL_NI3: chunk_mma<LDA, LDB, MI_N, 3, -64>(acc, ap, bp); break;
+    case SEL_TRI0: chunk_mma<LDA, LDB, MI_N, 4, 0>(acc, ap, bp); break;
+    case SEL_MLO2: chunk_mma<LDA, LDB, MI_N, 4, -64, 2>(acc, ap, bp); break;
+    case SEL_MLO2_NI3: chunk_mma<LDA, LDB, MI_N, 3, -64, 2>(acc, ap, bp); break;
+    case SEL_NLO2: chunk_mma<LDA, LDB, MI_N, 4, -64, 0, 2>(acc, ap, bp); break;
+    default: chunk_mma<LDA, LDB, MI_N, 4, -64>(acc, ap, bp); break;
   }
 }
 
@@ -163,7 +157,7 @@ __device__ __forceinline__ int sel_cols(int ni_lim) {
   return ni_lim <= 0 ? SEL_SKIP : ni_lim == 1 ? SEL_NI1 : ni_lim == 2 ? SEL_NI2 : ni_lim == 3 ? SEL_NI3 : SEL_FULL;
 }
 __device__ __forceinline__ int sel_rows(int mi_lim) {  // mi_lim is even (n is padded to 16-row chunks)
-  return mi_lim <= 0 ? SEL_SKIP : mi_lim == 2 ? SEL_MI2 : mi_lim == 4 ? SEL_MI4 : mi_lim == 6 ? SEL_MI6 : SEL_FULL;
+  return mi_lim <= 0 ? SEL_SKIP : mi_lim == 2 ? SEL_MI2 : SEL_FULL;
 }
 
 // Geometry of this CTA's half tile inside the 128x128 tile.
@@ -184,11 +178,13 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   constexpr int LDT = LDS_H;                      // parked half tile: k-major rows of 64
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t npad = g.npad;
-  // warp w runs on SMSP w.  ROWSPLIT: the four warps are the four 32-column groups of the 64-row half.
-  // COLSPLIT: two row groups x two column groups of the 64-column half.
-  const int wm = COLSPLIT ? (warp >> 1) : 0;
-  const int wn = COLSPLIT ? (warp & 1) : warp;
-  const int r0t = hg.r0h + wm * 64;          // tile-relative row of the warp tile's first row
+  // Eight consumer warps with 32 x 32 register tiles, two per SMSP (warps w and w + 4 share SMSP w mod 4): a CTA that is
+  // alone on its SM - the thin launches of small batches - still has a second warp per scheduler to fill the bubbles of
+  // the first (barrier waits, fragment-load latency at chunk boundaries).
+  // ROWSPLIT (64 x 128): 2 row groups x 4 column groups.  COLSPLIT (128 x 64): 4 row groups x 2 column groups.
+  const int wm = COLSPLIT ? (warp >> 1) : (warp >> 2);
+  const int wn = COLSPLIT ? (warp & 1) : (warp & 3);
+  const int r0t = hg.r0h + wm * WROWS;       // tile-relative row of the warp tile's first row
   const int gq = lane >> 2, t = lane & 3;
   const bool fwd = g.mode == GEMM_FWD_ROW;
   // Column layout.  Default: column group wn owns the four 8-column blocks at 32 wn.  FWD_ROW tiles with fewer than 64
@@ -203,19 +199,53 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     cbase = wn == 0 ? 0 : 8 * w0;
   }
   const int c0t = hg.c0h + cbase;             // tile-relative column of the warp tile's first column
-  const int mi_valid = RAGGED ? min(8, max(0, (rows_valid - r0t + 7) / 8)) : 8;
-  const int row0 = wm * 64 + gq;  // + mi*8 : A-operand row inside the chunk
+  const int mi_valid = RAGGED ? min(MI_N, max(0, (rows_valid - r0t + 7) / 8)) : MI_N;
+  const int row0 = wm * WROWS + gq;  // + mi*8 : A-operand row inside the chunk
   const int col0 = cbase + gq;    // + ni*8 : B-operand row inside the chunk
+
+  // ---- operand traffic: ONE tensor-map TMA request (cp.async.bulk.tensor.3d, SASS UTMALDG) lands a whole operand chunk.
+  // The box is KT columns x the PADDED row count (132 / 68), so the dense box pitch IS the bank-conflict-free padded
+  // pitch of the fragment loads (the 4 extra rows per column are never read).  Round 1 issued one 1 KB bulk copy per
+  // operand column (32 requests per chunk) from a dedicated producer warp; with two requests per chunk the issue is
+  // folded into consumer warp 0: after it has released a stage it waits until the other seven warps have too and
+  // refills it, its SMSP partner (warp 4) keeps the DMMA pipe busy meanwhile - no producer warpgroup, 128 registers
+  // for every thread at two CTAs per SM.
+  const CUtensorMap* mapA_L = COLSPLIT ? &g.tm_L132 : &g.tm_L68;
+  const CUtensorMap* mapA_D = COLSPLIT ? &g.tm_DT132 : &g.tm_DT68;
+  const CUtensorMap* mapB_L = COLSPLIT ? &g.tm_L68 : &g.tm_L132;
+  const CUtensorMap* mapB_D = COLSPLIT ? &g.tm_DT68 : &g.tm_DT132;
+  auto issue_main = [&](int c) {  // main-loop chunk c -> stage c % NSTAGE (called by lane 0 of warp 0)
+    const int stage = c % NSTAGE, kb = tc.kb0 + c / (NB / KT), kc = kb * NB + (c % (NB / KT)) * KT;
+    const CUtensorMap* ma; const CUtensorMap* mb; int ra, rb, gb = gp;
+    if (kb == tc.a_diag_kb) { ma = mapA_D; ra = hg.r0h; }
+    else { ma = mapA_L; ra = tc.i * NB + hg.r0h; }
+    if (kb == tc.b_diag_kb) { mb = mapB_D; rb = hg.c0h; }
+    else if (fwd) { mb = &g.tm_T68; rb = hg.gcol_off; gb = gp - g.t_gp_off; }
+    else { mb = mapB_L; rb = tc.j * NB + hg.c0h; }
+    mbar_expect_tx(&full[stage], STAGE_DOUBLES * sizeof(double));
+    double* dst = stages + stage * STAGE_DOUBLES;
+    tma_load_3d(dst, ma, ra, kc, gp, &full[stage]);
+    tma_load_3d(dst + KT * LDA, mb, rb, kc, gb, &full[stage]);
+  };
+  auto issue_r = [&](int c) {  // chunk c of the post-multiplier inv(L_rblk) -> rbuf[c % NRBUF]
+    const int buf = c % NRBUF;
+    mbar_expect_tx(&rfull[buf], RBUF_DOUBLES * sizeof(double));
+    tma_load_3d(rbuf + buf * RBUF_DOUBLES, &g.tm_D132, 0, tc.rblk * NB + c * KT, gp, &rfull[buf]);
+  };
+  if (warp == 0 && lane == 0) {  // prologue: fill the ring, start the post-multiplier
+    for (int c = 0; c < min(NSTAGE, nchunks); ++c) issue_main(c);
+    if (tc.post) for (int c = 0; c < NRBUF; ++c) issue_r(c);
+  }
 
   // The accumulators start at -Cin (Cholesky tiles: K(i,j); FWD_ROW: the right-hand-side block), loaded straight
   // into the accumulator registers while the first operand chunks are still in flight.  After the k-loop
   // acc = sum - Cin = -(Cin - sum); the sign is folded into the stores below.
   const int64_t grow = (int64_t)tc.i * NB, gcol = fwd ? (int64_t)hg.gcol_off : (int64_t)tc.j * NB;
-  double acc[8][4][2];
+  double acc[MI_N][4][2];
   if (fwd) {
     const double* Tin = g.Tm + (int64_t)(gp - g.t_gp_off) * g.t_stride + gcol + grow * g.ldt;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const int r = r0t + mi * 8 + gq, cc = c0t + ni * 8 + 2 * t;
@@ -227,7 +257,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   } else if (tc.use_cin) {
     const double* Cin = g.Cin + (int64_t)gp * g.mat_stride + grow + gcol * npad;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const int r = r0t + mi * 8 + gq, cc = c0t + ni * 8 + 2 * t;
@@ -237,7 +267,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
       }
   } else {
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
   }
@@ -259,7 +289,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   // (decided per TILE: the mirror partner of a block may live in the other half, so a ragged tile - last block row - is
   // computed and stored in full by both of its halves, also by the half whose own rows are all valid)
   const bool lsym = rows_valid == NB && g.mode == GEMM_LAUUM && tc.i == tc.j;
-  const int sel_tri = diag_off >= 8 ? SEL_SKIP : diag_off == 4 ? SEL_TRI4 : diag_off == 0 ? SEL_TRI0 : SEL_FULL;
+  const int sel_tri = diag_off >= MI_N ? SEL_SKIP : diag_off == 0 ? SEL_TRI0 : SEL_FULL;  // diag_off is a multiple of 4
   const int sel_plain = ni_lim < 4 ? sel_cols(ni_lim) : sel_rows(mi_valid);  // column-limited bodies run all 8 row slabs
   {
     int stage = 0; uint32_t phase = 0;
@@ -284,6 +314,10 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
       chunk_dispatch<LDA, LDB>(sel, acc, As + t * LDA + row0, As + KT * LDA + t * LDB + col0);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
+      if (warp == 0 && c + NSTAGE < nchunks) {  // refill: every consumer warp has released this stage
+        mbar_wait(&empty[stage], phase);
+        if (lane == 0) issue_main(c + NSTAGE);
+      }
       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
     }
   }
@@ -305,7 +339,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
       else { out = g.KinvD + (int64_t)gp * g.dinv_stride + (int64_t)tc.i * NB * NB; ldo = NB; }
     }
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         if (RAGGED && mi >= mi_valid) continue;
@@ -325,26 +359,26 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
   double* Ts = stages;
   if (tc.post == 1) {  // ROWSPLIT.  A operand: Ts[k][m] = T[m][k], m = the half's 64 rows, k = the tile's 128 columns
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int r = wm * 64 + mi * 8 + gq, cc = cbase + ni * 8 + 2 * t;
+        const int r = wm * WROWS + mi * 8 + gq, cc = cbase + ni * 8 + 2 * t;
         const bool ok = !RAGGED || mi < mi_valid;  // skipped rows are parked as zeros (finite operands for the second pass)
         Ts[cc * LDT + r] = ok ? acc[mi][ni][0] : 0.0;
         Ts[(cc + 1) * LDT + r] = ok ? acc[mi][ni][1] : 0.0;
       }
   } else {  // COLSPLIT.  B operand: Ts[k][n] = T[k][n], k = the tile's 128 rows, n = the half's 64 columns
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int r = wm * 64 + mi * 8 + gq, cc = cbase + ni * 8 + 2 * t;
+        const int r = wm * WROWS + mi * 8 + gq, cc = cbase + ni * 8 + 2 * t;
         const bool ok = !RAGGED || mi < mi_valid;
         if (ni < ni_lim) *reinterpret_cast<double2*>(&Ts[r * LDT + cc]) = ok ? make_double2(acc[mi][ni][0], acc[mi][ni][1]) : make_double2(0.0, 0.0);
       }
   }
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi)
+  for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
   named_bar_sync(1, N_CONSUMER_WARPS * 32);
@@ -352,7 +386,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
 
   // Dinv is lower triangular: R[x][k] == 0 for k > x.  post 1: x = output column, post 2: x = output row
   // (tile-relative; the post-multiplier chunk c covers k = 16c .. 16c + 15 of the whole tile).
-  const int kmax = (tc.post == 1) ? (c0t + 31) : min(r0t + 63, rows_valid - 1);
+  const int kmax = (tc.post == 1) ? (c0t + 31) : min(r0t + WROWS - 1, rows_valid - 1);
   for (int c = 0; c < NB / KT; ++c) {
     const int buf = c % NRBUF;
     mbar_wait(&rfull[buf], (c / NRBUF) & 1);
@@ -365,22 +399,26 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
         if (sel_plain == SEL_FULL && 2 * c - c0t / 8 == 2) sel = SEL_NLO2;
         chunk_dispatch<LDA, LDB>(sel, acc, Tc + row0, Rs + c0t + gq);
       } else {             // out(128 x 64) = R(128 x 128) * T(128 x 64) : A = R chunk (128-wide rows), B = parked T (64-wide rows)
-        const int lo = 2 * c - r0t / 8;  // first 8-row slab that meets chunk c: 0, 2, 4 or 6 here (c * KT <= kmax)
+        const int lo = 2 * c - r0t / 8;  // first 8-row slab that meets chunk c: 0 or 2 here (c * KT <= kmax)
         if (lo > 0) {
-          if (sel_plain == SEL_FULL) sel = lo == 2 ? SEL_MLO2 : lo == 4 ? SEL_MLO4 : SEL_MLO6;
-          else if (sel_plain == SEL_NI3) sel = lo == 2 ? SEL_MLO2_NI3 : lo == 4 ? SEL_MLO4_NI3 : SEL_MLO6_NI3;
+          if (sel_plain == SEL_FULL) sel = SEL_MLO2;
+          else if (sel_plain == SEL_NI3) sel = SEL_MLO2_NI3;
         }
         chunk_dispatch<LDA, LDB>(sel, acc, Rs + r0t + gq, Tc + col0);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rempty[buf]);
+    if (warp == 0 && c + NRBUF < NB / KT) {
+      mbar_wait(&rempty[buf], (c / NRBUF) & 1);
+      if (lane == 0) issue_r(c + NRBUF);
+    }
   }
   GPRB_TL(5);
 
   if (tc.post == 1) {
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         if (RAGGED && mi >= mi_valid) continue;
@@ -392,7 +430,7 @@ __device__ __forceinline__ void consume_tile(const GemmArgs& g, const TileCoord&
     double* outp = fwd ? g.Tm + (int64_t)(gp - g.t_gp_off) * g.t_stride + gcol + grow * g.ldt : Cout + gcol + grow * npad;
     const int64_t ldo = fwd ? g.ldt : npad;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI_N; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         if ((RAGGED && mi >= mi_valid) || ni >= ni_lim) continue;
@@ -448,54 +486,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_tile_gemm(const __grid_cons
   }
   __syncthreads();
 
-  if (warp >= N_CONSUMER_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");  // whole producer warpgroup; frees registers for the consumers
-    if (warp != N_CONSUMER_WARPS) return;
-    // ===================== producer warp =====================
-    // ONE tensor-map TMA request (cp.async.bulk.tensor.3d, SASS UTMALDG) lands a whole operand chunk: the box is KT
-    // columns x the PADDED row count (132 / 68), so the dense box pitch IS the bank-conflict-free padded pitch of the
-    // fragment loads (the 4 extra rows per column are never read).  Round 1 issued one 1 KB bulk copy per operand column
-    // (32 requests per chunk); at two CTAs per SM that request rate became the limiter of the k-loop.
-    int stage = 0; uint32_t phase = 0;
-    int rissued = 0;
-    auto issue_r = [&](int c) {  // chunk c of the post-multiplier -> rbuf[c % NRBUF]
-      const int buf = c % NRBUF;
-      mbar_wait(&rempty[buf], ((c / NRBUF) & 1) ^ 1);
-      if (lane == 0) {
-        mbar_expect_tx(&rfull[buf], RBUF_DOUBLES * sizeof(double));
-        tma_load_3d(rbuf + buf * RBUF_DOUBLES, &g.tm_D132, 0, tc.rblk * NB + c * KT, gp, &rfull[buf]);
-      }
-    };
-    int issued = 0;  // main chunks issued so far; the post-multiplier prefetch follows the first ring fill
-    const CUtensorMap* mapA_L = COLSPLIT ? &g.tm_L132 : &g.tm_L68;
-    const CUtensorMap* mapA_D = COLSPLIT ? &g.tm_DT132 : &g.tm_DT68;
-    const CUtensorMap* mapB_L = COLSPLIT ? &g.tm_L68 : &g.tm_L132;
-    const CUtensorMap* mapB_D = COLSPLIT ? &g.tm_DT68 : &g.tm_DT132;
-    for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
-      // operand sources as (tensor map, row coordinate, GP coordinate); the column coordinate is the k index
-      const CUtensorMap* ma; const CUtensorMap* mb; int ra, rb, gb = gp;
-      if (kb == tc.a_diag_kb) { ma = mapA_D; ra = hg.r0h; }
-      else { ma = mapA_L; ra = tc.i * NB + hg.r0h; }
-      if (kb == tc.b_diag_kb) { mb = mapB_D; rb = hg.c0h; }
-      else if (fwd) { mb = &g.tm_T68; rb = hg.gcol_off; gb = gp - g.t_gp_off; }
-      else { mb = mapB_L; rb = tc.j * NB + hg.c0h; }
-      const int cend = (kb == g.J - 1) ? last_kb_chunks : NB / KT;
-      for (int c = 0; c < cend; ++c) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        if (lane == 0) {
-          mbar_expect_tx(&full[stage], STAGE_DOUBLES * sizeof(double));
-          double* dst = stages + stage * STAGE_DOUBLES;
-          tma_load_3d(dst, ma, ra, kb * NB + c * KT, gp, &full[stage]);
-          tma_load_3d(dst + KT * LDA, mb, rb, kb * NB + c * KT, gb, &full[stage]);
-        }
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-        if (++issued == NSTAGE && tc.post) { for (; rissued < NRBUF; ++rissued) issue_r(rissued); }
-      }
-    }
-    if (tc.post) for (; rissued < NB / KT; ++rissued) issue_r(rissued);
-    return;
-  }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // consumer warpgroup
   // RAGGED whenever the warp tiles of this half do not all have 64 valid rows
   const int rows_here = rows_valid - hg.r0h;  // valid rows from the half's first row on (ROWSPLIT: up to 64 matter)
   const bool ragged = COLSPLIT ? (rows_valid < NB) : (rows_here < HB);
