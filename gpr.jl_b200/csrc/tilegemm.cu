@@ -13,14 +13,17 @@
 // DMMA pipe idle - 8-17 us per tile against k-loops of 16.6 us per 128-block (profiles/r01_gemm_tile_timeline.log).
 // Half tiles need 108 KB: two CTAs share an SM and the fill / park / store of one runs under the k-loop of the
 // other.  Launches with fewer tiles than SMs (the serial CHOL_DIAG chain, small batches, the reference's one-GP-at-
-// a-time pattern) get twice the CTAs, each with an SMSP's DMMA pipe to itself.
+// a-time pattern) get twice the CTAs.
 //
-// Warp-specialised: warps 0-3 are DMMA consumers with 64x32 register tiles (mma.sync.m8n8k4.f64 -> SASS
-// DMMA.8x8x4, the native fp64 tensor shape on sm_100a; tcgen05 has no f64 kind), one per SMSP; warp 4 is the
-// producer (ONE tensor-map TMA request per operand chunk - SASS UTMALDG - completion counted on mbarriers); warps
-// 5-7 only exist to complete its warpgroup.  Register reallocation (setmaxnreg): the CTA launches with 128
-// registers per thread (2 CTAs x 256 threads x 128 = the whole register file), the producer warpgroup shrinks and
-// the consumer warpgroup grows, so the A/B fragments stay double-buffered a whole k4-step ahead.
+// Eight DMMA consumer warps with 32x32 register tiles (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, the native fp64 tensor
+// shape on sm_100a; tcgen05 has no f64 kind), two per SMSP, and NO producer warp: a whole operand chunk arrives with
+// ONE tensor-map TMA request (cp.async.bulk.tensor.3d, SASS UTMALDG; completion counted on mbarriers), so the two
+// requests of a chunk are issued by lane 0 of consumer warp 0 right after the stage they refill has been released by
+// all eight warps.  256 threads x 2 CTAs leave 128 registers per thread: accumulators (64) plus A/B fragments
+// double-buffered a k4-step ahead fit without spills.  Measured steps of this design at B = 400 GPs, n = 2000:
+// full tiles + producer warp (round 1) 119.1 ms, half tiles with four 64x32 consumer warps 119.5 ms (a lone warp per
+// SMSP leaves bubbles at every chunk boundary, and co-resident CTAs of one launch run in lockstep), eight 32x32 warps
+// 115.1 ms.
 // Padded smem rows (132 / 68 doubles, both = 4 mod 16) make every fragment load bank-conflict free.
 //
 // Modes (tile coordinates and k-range derive from `mode`, `step` and blockIdx.x):
