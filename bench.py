@@ -4,16 +4,24 @@
 Workload (config.workload): the CP cartpole noise experiment shape - n=2000 training states, d=26 (two bodies x 13
 CState entries), G=4 output GPs per trial, 100 trial datasets -> B=400 independent GPs per GPU.  One *step* = one
 logML+gradient evaluation of all B GPs (assembly -> Cholesky -> solve -> inverse -> fused gradient), at a fresh theta
-per step (theta_0 + seeded perturbations).  Multi-GPU (torchrun): every rank owns its own 100 trials (weak scaling,
-no data-path collective) and a per-step NCCL all-gather of the per-GP results stands in for the reference's result
-callbacks (examples/parallel/core.jl:47-56).
+per step (theta_0 + seeded perturbations).
+
+Multi-GPU (torchrun): `--scaling weak` (default, what the driver runs) gives every rank its own 100 trials; `--scaling
+strong` splits the SAME 100 trials round-robin over the ranks (north_star: "100 trial datasets batched across 8xB200";
+the reference's jobid axis, examples/parallel/core.jl:28).  No data-path collective; the per-step gather of the
+per-GP results stands in for the reference's result callbacks (core.jl:47-56) - torch's NCCL all-gather of the device
+tensors in the `value` leg, gprb_gather (ncclAllGather inside libgprb200.so) of the host rows in the `e2e` leg.
 
   value  : inputs (X, y, theta) resident in HBM before the timed region (gprb_eval_device), CUDA events, max over ranks
   e2e    : the public API call GPBatch.eval() with HOST buffers; every step re-uploads X, y and theta and reads
            mll + grad back (host<->device copies inside the timed region)
   roofline: the DMMA tile-GEMM kernel (k_tile_gemm), algorithmic n^3 flops per evaluation / summed launch time
-  cpu_baseline / --impl reference: the oracle (restated reference path, scipy OpenBLAS) on ALL host cores, organised like
-           the reference (trials in parallel, examples/parallel/core.jl:28): one worker process per core, 1 BLAS thread each.
+  predict: predict_y samples/s (m = 100 test states per GP, mean+variance and mean only) with its own roofline
+           (F_pred = n^2 + (3d+4) n flops per sample), device time from CUDA events on the library's prediction stream
+  config.info_histogram: per-GP make_posdef! status of the timed step (how many GPs needed jitter retries)
+  cpu_baseline / --impl reference: the oracle (restated reference path, scipy OpenBLAS) on the host cores in both
+           arrangements SURVEY.md 8d asks for: one worker process per core with 1 BLAS thread each (trials in parallel like
+           core.jl:28; this is the reported value) and one process with all-threads BLAS.
 """
 import argparse
 import json
@@ -216,6 +224,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.environ["GPRB200_REUSE"] = "0"  # no resident-state reuse inside the benchmark: every step is a full evaluation
     import gpr_jl_b200 as G
