@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <limits>
 #include <new>
 
@@ -103,8 +104,12 @@ static void free_batch(gprb_batch* b) {
 // entries of the segment (the host orders value+gradient GPs first); assembly, Cholesky and solve for all entries but
 // the first `nreuse` (<= ngrad), whose factor, alpha and mll of the previous evaluation at the same theta are still
 // resident (the optimiser asks for the gradient at the point its line search just accepted).
+// `ops` != nullptr: the launches are not issued but appended (as closures) to `ops`, so that run_pipeline can issue the
+// launches of all stream groups interleaved - every group then starts at once instead of one enqueue time (0.3 ms of host
+// work per group) after the previous one, which matters for short passes (50 GPs per GPU in the 8-GPU strong split).
+using LaunchOps = std::vector<std::function<int()>>;
 static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nreuse, bool right_looking, cudaStream_t st,
-                            bool prof) {
+                            bool prof, LaunchOps* ops = nullptr) {
   if (count <= 0) return 0;
   const bool with_grad = ngrad > 0;
   const int32_t* glist = b->list + off;     // inverse + gradient: glist[0 .. ngrad)
@@ -115,9 +120,13 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   int rc;
   int64_t& launches = b->ctx->launches;
   int gcount = count;  // GPs per tile-GEMM launch (count for the factorisation, ngrad for the inverse)
+  auto run = [&](std::function<int()> f) -> int {
+    if (ops) { ops->push_back(std::move(f)); return 0; }
+    return f();
+  };
   auto gemm = [&](const GemmArgs& a, int ntiles) -> int {
     const int count = gcount;
-    if (!prof) return launch_tile_gemm(a, ntiles, count, st);
+    if (!prof) return run([a, ntiles, count, st] { return launch_tile_gemm(a, ntiles, count, st); });
     while ((int)b->gemm_ev.size() < b->gemm_ev_used + 2) {
       cudaEvent_t e;
       if (cudaEventCreate(&e) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
@@ -167,7 +176,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   // whose launches are short and wide, instead of the left-looking one, whose k-loops grow with the column index.
   AssembleArgs aa{b->Xtptr, b->theta, b->jitter, b->A, nullptr, b->fail, list, ms, (int)b->n, (int)b->npad, b->d, J, b->kind};
   if (right_looking) aa.A2 = b->Lm;
-  if ((rc = launch_assemble(aa, count, st))) return rc;
+  if ((rc = run([aa, count, st] { return launch_assemble(aa, count, st); }))) return rc;
   ++launches;
   if (prof) cudaEventRecord(b->ev[1], st);
   DiagArgs da{nullptr, b->Lm, b->Dinv, b->DinvT, b->logdet_part, b->fail, list, ms, dstride, (int)b->npad, J, 0, nv};
@@ -181,7 +190,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
     }
     da.step = j;
     da.Src = (!right_looking && j == 0) ? b->A : nullptr;
-    if ((rc = launch_diag_factor(da, count, st))) return rc;
+    if ((rc = run([da, count, st] { return launch_diag_factor(da, count, st); }))) return rc;
     ++launches;
     if (j + 1 < J) {
       ga.mode = right_looking ? GEMM_CHOL_PANEL : GEMM_CHOL_COL;
@@ -198,7 +207,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   SolveArgs sa{b->Lm, b->Dinv, b->ymm, b->logdet_part, b->fail, b->zbuf, b->alpha, b->mll, list, ms, dstride,
                (int)b->n, (int)b->npad, J, nv};
   sa.cluster_below = b->solve_cluster_below;
-  if ((rc = launch_solve(sa, count, st))) return rc;
+  if ((rc = run([sa, count, st] { return launch_solve(sa, count, st); }))) return rc;
   ++launches;
   }
   if (prof) cudaEventRecord(b->ev[3], st);
@@ -217,7 +226,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
     if (prof) cudaEventRecord(b->ev[4], st);
     GradArgs gr{b->Xtptr, b->theta, b->A, b->KinvD, b->alpha, b->grad_part, b->grad, b->fail, glist, ms, dstride,
                 (int)b->n, (int)b->npad, b->d, J, b->kind};
-    if ((rc = launch_grad(gr, ngrad, st))) return rc;
+    if ((rc = run([gr, ngrad, st] { return launch_grad(gr, ngrad, st); }))) return rc;
     launches += 2;
     if (prof) cudaEventRecord(b->ev[5], st);
   }
@@ -285,14 +294,21 @@ static int run_pipeline(gprb_batch* b, const std::vector<Group>& groups) {
     return 0;
   }
   GPRB_CUDA(cudaEventRecord(b->join[0], b->stream[0]));
+  std::vector<LaunchOps> ops(groups.size());
+  size_t longest = 0;
   for (size_t s = 0; s < groups.size(); ++s) {
     const Group& g = groups[s];
     if (s > 0) GPRB_CUDA(cudaStreamWaitEvent(b->stream[s], b->join[0], 0));
-    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[s], false))) return rc;
-    if (s > 0) {
-      GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
-      GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
-    }
+    if ((rc = enqueue_pipeline(b, g.off, g.count, g.ngrad, g.nreuse, g.rl, b->stream[s], false, groups.size() > 1 ? &ops[s] : nullptr)))
+      return rc;
+    longest = std::max(longest, ops[s].size());
+  }
+  for (size_t k = 0; k < longest; ++k)  // launch k of every group, group by group: all groups advance together
+    for (size_t s = 0; s < groups.size(); ++s)
+      if (k < ops[s].size() && (rc = ops[s][k]())) return rc;
+  for (size_t s = 1; s < groups.size(); ++s) {
+    GPRB_CUDA(cudaEventRecord(b->join[s], b->stream[s]));
+    GPRB_CUDA(cudaStreamWaitEvent(b->stream[0], b->join[s], 0));
   }
   return 0;
 }
