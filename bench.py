@@ -401,8 +401,8 @@ def main():
     traffic, traffic_src = None, None
     if n == N_TRAIN and T == TRIALS and args.system == SYSTEM:  # ncu dram__bytes_read+write per launch, captured at exactly this configuration
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_traffic.json (tools/traffic.sh: ncu dram bytes, mean of the 47 launches of one evaluation)"
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r02_traffic.json (tools/traffic.sh: ncu dram bytes, mean of the 46 launches of one evaluation)"
         except Exception:
             pass
     roof = {"bound": "tensor", "kernel": "k_tile_gemm (fp64 DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

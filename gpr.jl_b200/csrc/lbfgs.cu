@@ -271,10 +271,15 @@ int batched_lbfgs(int B, int P, double* theta_inout, const gprb_lbfgs_opts& o, c
       break;
     }
   }
-  // ---- write the minimiser back and leave the device state evaluated there (optimize! -> update_target!)
+  // ---- write the minimiser back and leave the device state evaluated there (optimize! -> update_target!).
+  // The state is left WITH the inverse (a value+gradient evaluation): for a GP that stopped right after a gradient
+  // evaluation - the normal case - that state is still resident and the evaluation costs nothing (state reuse); for the
+  // others it is one extra inverse + gradient per GP, and in return the reference's next call, predict_y(gp, obs) with
+  // one test column (examples/utils/predictdynamics.jl:13), always finds V = L^-T resident (0.11 ms instead of 0.7 ms).
+  // mll is bit-identical either way (same factorisation).
   for (int b = 0; b < B; ++b) {
     memcpy(&theta[(size_t)b * P], S[b].x.data(), sizeof(double) * P);
-    act[b] = 1;
+    act[b] = 2;
   }
   if ((rc = eval_all())) return rc;
   memcpy(theta_inout, theta.data(), sizeof(double) * B * P);
