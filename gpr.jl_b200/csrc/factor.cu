@@ -30,19 +30,39 @@ __device__ __forceinline__ void slab_mma(double (&acc)[4][2], const double* Abas
   }
 }
 
+// Same product with the B operand stored the other way round: B(n,k) = Bbase[n*ldb + k] (a column-major sub-block read as
+// its own transpose).  Bank pattern of a half-warp: (4g + t) mod 16 with ldb = 36 - conflict-free like the k-major form.
+__device__ __forceinline__ void slab_mma_bt(double (&acc)[4][2], const double* Abase, int lda, const double* Bbase, int ldb,
+                                            int ksteps, int g, int t) {
+  for (int k4 = 0; k4 < ksteps; ++k4) {
+    const double a = Abase[(k4 * 4 + t) * lda + g];
+    const double* bp = Bbase + g * ldb + k4 * 4 + t;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) dmma884(acc[ni][0], acc[ni][1], a, bp[ni * 8 * ldb]);
+  }
+}
+
+// Packed lower-triangular storage of the 128x128 block in shared memory: the ten 32x32 sub-blocks (bi >= bj), each
+// column-major with the padded stride LDW = 36.  90 KB per CTA instead of the 195 KB of a padded square plus side
+// buffers: TWO blocks are factorised per SM at a time (the serial 32x32 potf2 + trtri of one overlaps the DMMA phases of
+// the other), and a factorisation can share an SM with a k_tile_gemm CTA (110.7 KB) of another stream group instead of
+// waiting for both of its CTAs to drain.
+constexpr int SBLK = SB * LDW;                     // doubles of one sub-block slot
+constexpr int NSLOT = NSB * (NSB + 1) / 2;         // 10
+__device__ __forceinline__ int slot_of(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * SBLK; }
+
 // One CTA per GP.  On entry Lm(j,j) holds S = K(j,j) - sum_k L(j,k) L(j,k)^T (lower part valid).
 // On exit: Lm(j,j) = L_jj, Dinv[j] = inv(L_jj), DinvT[j] = inv(L_jj)^T, logdet_part[j] = sum log diag(L_jj),
 // fail = LAPACK-style info (first non-positive / NaN pivot, 1-based) when the block is not positive definite.
 //
 // Blocked inside shared memory with 32x32 sub-blocks: the sub-block on the diagonal is factorised and inverted by
 // ONE warp entirely in registers (row per lane, pivots broadcast by shuffles); panel solves, trailing updates and
-// the blocked triangular inverse are 8x32 DMMA slabs spread over the 8 warps.  S (col-major, ld 132) ends up as
-// [ L off-diagonal sub-blocks (lower) | W^T = inv(L)^T (upper, diagonal sub-blocks included) ].
-__global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
+// the blocked triangular inverse are 8x32 DMMA slabs spread over the 8 warps.  Everything is in place: slot (i,j), i > j,
+// holds S(i,j), then L(i,j) (written to HBM at the end of phase A), then W(i,j) = inv(L)(i,j) stored ROW-major (the B operand
+// of the later block rows); slot (j,j) holds S(j,j), then W(j,j) column-major (L(j,j) goes to HBM from registers).
+__global__ void __launch_bounds__(DIAG_THREADS, 2) k_diag_factor(DiagArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* S = reinterpret_cast<double*>(smem_raw);   // S(r,c) = S[c*LDS_T + r]
-  double* Dd = S + NB * LDS_T;                        // [NSB][SB*LDW]  W_dd col-major: Dd[r + c*LDW]
-  double* Tb = Dd + NSB * SB * LDW;                   // [NSB-1][SB*LDW] scratch T(k,n) = Tb[k*LDW + n]
+  double* S = reinterpret_cast<double*>(smem_raw);   // [NSLOT][SBLK]
   __shared__ int bad_col;
   __shared__ double dinv32[SB];
   const int gp = g.list ? g.list[blockIdx.x] : blockIdx.x;
@@ -55,10 +75,29 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
   double* T = g.Lm + (int64_t)gp * g.mat_stride + (int64_t)j * NB + (int64_t)j * NB * npad;
   const double* Tsrc = g.Src ? g.Src + (int64_t)gp * g.mat_stride + (int64_t)j * NB + (int64_t)j * NB * npad : T;
   // rows / cols beyond nv are padding the GEMM stages neither compute nor read: treat them as the identity here
+  // (nv is a multiple of 16: a pair of rows (r, r + 1), r even, is valid or padding as a whole)
   const int nvl = (j == g.J - 1) ? g.nv - j * NB : NB;
-  for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-    const int r = idx & (NB - 1), c = idx >> 7;
-    S[c * LDS_T + r] = (r < nvl && c < nvl) ? Tsrc[r + c * npad] : (r == c ? 1.0 : 0.0);
+  {
+    // lower sub-blocks only, 16-byte loads, all of a thread's loads in flight at once (the read is pure latency otherwise)
+    constexpr int PAIRS = NSLOT * SB * SB / 2, PER_THREAD = PAIRS / DIAG_THREADS;  // 5120 pairs, 20 per thread
+    constexpr int BATCH = PER_THREAD / 2;  // two batches of ten loads: 40 data registers in flight
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double2 v[BATCH];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int idx = tid + (h * BATCH + u) * DIAG_THREADS, p = idx >> 9, w = idx & 511;  // 512 row pairs per sub-block
+        const int bi = p < 1 ? 0 : p < 3 ? 1 : p < 6 ? 2 : 3, bj = p - bi * (bi + 1) / 2;
+        const int r = bi * SB + 2 * (w & 15), c = bj * SB + (w >> 4);
+        v[u] = (r < nvl && c < nvl) ? *reinterpret_cast<const double2*>(Tsrc + r + c * npad)
+                                    : make_double2(r == c ? 1.0 : 0.0, r + 1 == c ? 1.0 : 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int idx = tid + (h * BATCH + u) * DIAG_THREADS, p = idx >> 9, w = idx & 511;
+        *reinterpret_cast<double2*>(&S[p * SBLK + (w >> 4) * LDW + 2 * (w & 15)]) = v[u];
+      }
+    }
   }
   if (tid == 0) bad_col = 0;
   __syncthreads();
@@ -68,6 +107,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
 #pragma unroll 1
   for (int jj = 0; jj < NSB; ++jj) {  // not unrolled: the straight-line sub-block code below is reused by all four iterations
     const int j0 = jj * SB;
+    double* D = S + slot_of(jj, jj);  // D(r,c) = D[c*LDW + r]
     if (warp_u == 0) {  // provably warp-uniform branch: the shuffles below compile to plain SHFL (no collective wrappers)
       // ---- A1: potf2 + trtri of the 32x32 diagonal sub-block by one warp, entirely in registers.
       // This is the serial critical path of the whole block (7 warps wait), so it is written for latency:
@@ -76,10 +116,9 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
       //   trtri  column-oriented forward substitution, lane c owns column c of W = inv(L_dd); L(r,k) is a
       //          broadcast shared-memory read, all updates of one step are independent FMAs
       // Both are straight-line (fully unrolled, ~3.5k instructions, reused by the four sub-block iterations).
-      double* D = S + j0 * LDS_T + j0;  // D(r,c) = D[c*LDS_T + r]
       double a[SB];
 #pragma unroll
-      for (int c = 0; c < SB; ++c) a[c] = D[c * LDS_T + lane];
+      for (int c = 0; c < SB; ++c) a[c] = D[c * LDW + lane];
       int bad = 0;
       double mydinv = 1.0;  // lane c ends up with 1 / L_cc
 #pragma unroll
@@ -102,7 +141,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
 #pragma unroll
       for (int c = 0; c < SB; ++c) {
         const double v = (lane >= c) ? a[c] : 0.0;
-        D[c * LDS_T + lane] = v;
+        D[c * LDW + lane] = v;
         T[(j0 + lane) + (int64_t)(j0 + c) * npad] = v;
       }
       dinv32[lane] = mydinv;
@@ -115,29 +154,27 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
       for (int k = 0; k < SB; ++k) {
         w[k] *= dinv32[k];
 #pragma unroll
-        for (int r = k + 1; r < SB; ++r) w[r] = fma(-D[k * LDS_T + r], w[k], w[r]);  // L(r,k): broadcast read
+        for (int r = k + 1; r < SB; ++r) w[r] = fma(-D[k * LDW + r], w[k], w[r]);  // L(r,k): broadcast read
       }
       __syncwarp();
-      // finalise: D becomes W_dd^T (upper incl. diagonal, exact zeros below); Dd[jj] gets W_dd column-major
-      double* Dj = Dd + jj * SB * LDW;
+      // the slot becomes W_dd, column-major (exact zeros above the diagonal)
 #pragma unroll
-      for (int r = 0; r < SB; ++r) {
-        D[r * LDS_T + lane] = w[r];   // W^T(lane, r) = W(r, lane)
-        Dj[r + lane * LDW] = w[r];    // W(r, lane)
-      }
+      for (int r = 0; r < SB; ++r) D[r + lane * LDW] = w[r];
     }
     __syncthreads();
-    // ---- A2: panel  L(i, jj) = S(i, jj) * W_dd^T  for the rows below the sub-block; 8-row slabs over the warps
-    const int nslab_panel = (NB - j0 - SB) / 8;
-    for (int sl = warp; sl < nslab_panel; sl += DIAG_THREADS / 32) {
-      const int rbase = j0 + SB + sl * 8;
+    // ---- A2: panel  L(i, jj) = S(i, jj) * W_dd^T  for the sub-blocks below; 8-row slabs over the warps
+    // (slab `sl` of sub-block `bi` is read and written by the same warp only: in place)
+    const int nslab_panel = (NSB - 1 - jj) * (SB / 8);
+    for (int it = warp; it < nslab_panel; it += DIAG_THREADS / 32) {
+      const int sl = it & 3, bi = jj + 1 + (it >> 2);
+      double* P = S + slot_of(bi, jj) + sl * 8;
       double acc[4][2] = {};
-      slab_mma(acc, S + j0 * LDS_T + rbase, LDS_T, Dd + jj * SB * LDW, LDW, SB / 4, gq, t);
+      slab_mma(acc, P, LDW, D, LDW, SB / 4, gq, t);
       __syncwarp();
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        S[(j0 + ni * 8 + 2 * t) * LDS_T + rbase + gq] = acc[ni][0];
-        S[(j0 + ni * 8 + 2 * t + 1) * LDS_T + rbase + gq] = acc[ni][1];
+        P[(ni * 8 + 2 * t) * LDW + gq] = acc[ni][0];
+        P[(ni * 8 + 2 * t + 1) * LDW + gq] = acc[ni][1];
       }
     }
     __syncthreads();
@@ -149,13 +186,13 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
       int bi = 0;
       while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
       const int bk = blk - bi * (bi + 1) / 2;
-      const int r0 = (jj + 1 + bi) * SB + sl * 8, c0 = (jj + 1 + bk) * SB;
       double acc[4][2] = {};
-      slab_mma(acc, S + j0 * LDS_T + r0, LDS_T, S + j0 * LDS_T + c0, LDS_T, SB / 4, gq, t);
+      slab_mma(acc, S + slot_of(jj + 1 + bi, jj) + sl * 8, LDW, S + slot_of(jj + 1 + bk, jj), LDW, SB / 4, gq, t);
+      double* C = S + slot_of(jj + 1 + bi, jj + 1 + bk) + sl * 8;
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        S[(c0 + ni * 8 + 2 * t) * LDS_T + r0 + gq] -= acc[ni][0];
-        S[(c0 + ni * 8 + 2 * t + 1) * LDS_T + r0 + gq] -= acc[ni][1];
+        C[(ni * 8 + 2 * t) * LDW + gq] -= acc[ni][0];
+        C[(ni * 8 + 2 * t + 1) * LDW + gq] -= acc[ni][1];
       }
     }
     __syncthreads();
@@ -164,44 +201,97 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_diag_factor(DiagArgs g) {
     if (tid == 0) g.fail[gp] = j * NB + bad_col;
     return;
   }
-
-  // ================= phase B: blocked inverse, W(i,j) = -W_ii * sum_{k=j}^{i-1} L(i,k) W(k,j), kept as W^T =========
-  for (int i = 1; i < NSB; ++i) {
-    const int i0 = i * SB;
-    // B1: T_j (32x32) = L(i, j..i-1) * W(j..i-1, j)   -- one contiguous k-range thanks to the W^T layout of S
-    for (int it = warp; it < i * (SB / 8); it += DIAG_THREADS / 32) {
-      const int sl = it & 3, jb = it >> 2, j0 = jb * SB;
-      double acc[4][2] = {};
-      slab_mma(acc, S + j0 * LDS_T + i0 + sl * 8, LDS_T, S + j0 * LDS_T + j0, LDS_T, (i - jb) * (SB / 4), gq, t);
-      double* Tj = Tb + jb * SB * LDW;
+  // L's off-diagonal sub-blocks go to HBM now (phase B overwrites them), zeros into the upper sub-blocks of the tile
+  {
+    constexpr int NOFF = NSLOT - NSB;  // 6
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
-        *reinterpret_cast<double2*>(&Tj[(sl * 8 + gq) * LDW + ni * 8 + 2 * t]) = make_double2(acc[ni][0], acc[ni][1]);
+    for (int u = 0; u < NOFF * SB * SB / 2 / DIAG_THREADS; ++u) {  // 12 row pairs per thread
+      const int idx = tid + u * DIAG_THREADS, q = idx >> 9, w = idx & 511;
+      const int bi = q < 1 ? 1 : q < 3 ? 2 : 3, bj = q - (bi * (bi - 1)) / 2;
+      const int rr = 2 * (w & 15), cc = w >> 4;
+      const double2 v = *reinterpret_cast<const double2*>(&S[slot_of(bi, bj) + cc * LDW + rr]);
+      *reinterpret_cast<double2*>(T + (bi * SB + rr) + (int64_t)(bj * SB + cc) * npad) = v;
+      *reinterpret_cast<double2*>(T + (bj * SB + rr) + (int64_t)(bi * SB + cc) * npad) = make_double2(0.0, 0.0);
+    }
+  }
+
+  // ================= phase B: blocked inverse, W(i,j) = -W_ii * sum_{k=j}^{i-1} L(i,k) W(k,j) =========================
+  // At most 12 (slab, j) items per block row over the 8 warps: every warp keeps its (up to two) 8x32 results in registers
+  // across the barrier that separates the last read of a slot from its overwrite.
+  for (int i = 1; i < NSB; ++i) {
+    const int nit = i * (SB / 8);
+    double acc[2][4][2];
+    // B1: T_j (32x32) = L(i, j..i-1) * W(j..i-1, j); the k = j term reads the column-major diagonal slot transposed
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int it = warp + u * (DIAG_THREADS / 32);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[u][ni][0] = acc[u][ni][1] = 0.0;
+      if (it < nit) {
+        const int sl = it & 3, jb = it >> 2;
+        slab_mma_bt(acc[u], S + slot_of(i, jb) + sl * 8, LDW, S + slot_of(jb, jb), LDW, SB / 4, gq, t);
+        for (int k = jb + 1; k < i; ++k) slab_mma(acc[u], S + slot_of(i, k) + sl * 8, LDW, S + slot_of(k, jb), LDW, SB / 4, gq, t);
+      }
+    }
+    __syncthreads();  // every L(i, .) has been read: the slots of block row i now take T, stored T(k,n) at [k*LDW + n]
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int it = warp + u * (DIAG_THREADS / 32);
+      if (it < nit) {
+        const int sl = it & 3, jb = it >> 2;
+        double* Tj = S + slot_of(i, jb);
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          *reinterpret_cast<double2*>(&Tj[(sl * 8 + gq) * LDW + ni * 8 + 2 * t]) = make_double2(acc[u][ni][0], acc[u][ni][1]);
+      }
     }
     __syncthreads();
-    // B2: W(i,j) = -W_ii * T_j, stored transposed into the upper sub-block (j,i) of S
-    for (int it = warp; it < i * (SB / 8); it += DIAG_THREADS / 32) {
-      const int sl = it & 3, jb = it >> 2, j0 = jb * SB;
-      double acc[4][2] = {};
-      slab_mma(acc, Dd + i * SB * LDW + sl * 8, LDW, Tb + jb * SB * LDW, LDW, SB / 4, gq, t);
+    // B2: W(i,j) = -W_ii * T_j (every slab needs the whole T_j: results wait in registers for the barrier again)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
-        *reinterpret_cast<double2*>(&S[(i0 + sl * 8 + gq) * LDS_T + j0 + ni * 8 + 2 * t]) = make_double2(-acc[ni][0], -acc[ni][1]);
+    for (int u = 0; u < 2; ++u) {
+      const int it = warp + u * (DIAG_THREADS / 32);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[u][ni][0] = acc[u][ni][1] = 0.0;
+      if (it < nit) {
+        const int sl = it & 3, jb = it >> 2;
+        slab_mma(acc[u], S + slot_of(i, i) + sl * 8, LDW, S + slot_of(i, jb), LDW, SB / 4, gq, t);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int it = warp + u * (DIAG_THREADS / 32);
+      if (it < nit) {
+        const int sl = it & 3, jb = it >> 2;
+        double* Wj = S + slot_of(i, jb);  // W(i,j)(r,c) at [r*LDW + c]
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          *reinterpret_cast<double2*>(&Wj[(sl * 8 + gq) * LDW + ni * 8 + 2 * t]) = make_double2(-acc[u][ni][0], -acc[u][ni][1]);
+      }
     }
     __syncthreads();
   }
 
-  // ================= write-out =================
+  // ================= write-out: W = inv(L_jj) column-major into Dinv, its transpose into DinvT =================
   double* Dinv = g.Dinv + (int64_t)gp * g.dinv_stride + (int64_t)j * NB * NB;
   double* DinvT = g.DinvT + (int64_t)gp * g.dinv_stride + (int64_t)j * NB * NB;
-  for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-    const int r = idx & (NB - 1), c = idx >> 7;
-    const int br = r / SB, bc = c / SB;
-    // S(r,c): lower off-diagonal sub-blocks = L ; upper incl. diagonal sub-blocks = W^T
-    if (br > bc) T[r + c * npad] = S[c * LDS_T + r];
-    else if (br < bc) T[r + c * npad] = 0.0;
-    DinvT[idx] = (br <= bc) ? S[c * LDS_T + r] : 0.0;   // W^T(r,c)
-    Dinv[idx] = (br >= bc) ? S[r * LDS_T + c] : 0.0;    // W(r,c) = W^T(c,r)
+#pragma unroll 4
+  for (int idx = tid; idx < NB * NB / 2; idx += DIAG_THREADS) {  // (row pair, column) of the 128x128 outputs
+    const int r = 2 * (idx & 63), c = idx >> 6;
+    const int br = r / SB, bc = c / SB, rr = r & (SB - 1), cc = c & (SB - 1);
+    double2 w = make_double2(0.0, 0.0), wt = make_double2(0.0, 0.0);
+    if (br > bc) {          // W(r,c), W(r+1,c) from the row-major slot (br,bc)
+      const double* P = S + slot_of(br, bc);
+      w = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
+    } else if (br == bc) {  // diagonal slot, column-major: W(r..r+1, c) and W^T(r..r+1, c) = W(c, r..r+1)
+      const double* P = S + slot_of(br, br);
+      w = *reinterpret_cast<const double2*>(&P[cc * LDW + rr]);
+      wt = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
+    } else {                // W^T(r,c) = W(c,r), W(c,r+1) from the row-major slot (bc,br)
+      wt = *reinterpret_cast<const double2*>(&S[slot_of(bc, br) + cc * LDW + rr]);
+    }
+    *reinterpret_cast<double2*>(&Dinv[r + c * NB]) = w;
+    *reinterpret_cast<double2*>(&DinvT[r + c * NB]) = wt;
   }
   if (warp == 0) {
 #pragma unroll
@@ -442,7 +532,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_cluster(SolveArgs g, in
   }
 }
 
-constexpr size_t DIAG_SMEM = (size_t)(NB * LDS_T + NSB * SB * LDW + (NSB - 1) * SB * LDW) * sizeof(double);
+constexpr size_t DIAG_SMEM = (size_t)(NSLOT * SBLK) * sizeof(double);  // 92160 B: two CTAs per SM, or one next to a k_tile_gemm CTA
 
 // per-device opt-in, called by gprb_init for the device of every context (see configure_tile_gemm)
 int configure_diag_factor() {
