@@ -60,7 +60,7 @@ int make_tensor_map(CUtensorMap* map, const double* base, uint64_t rows, uint64_
 }
 
 static void set_gemm_maps(GemmArgs& ga, const gprb_batch* b) {
-  ga.tm_L132 = b->tm_L132; ga.tm_L68 = b->tm_L68; ga.tm_DT132 = b->tm_DT132; ga.tm_DT68 = b->tm_DT68; ga.tm_D132 = b->tm_D132;
+  ga.tm_L132 = b->tm_L132; ga.tm_L68 = b->tm_L68; ga.tm_A68 = b->tm_A68; ga.tm_DT132 = b->tm_DT132; ga.tm_DT68 = b->tm_DT68; ga.tm_D132 = b->tm_D132;
 }
 
 template <typename T>
@@ -171,6 +171,7 @@ static int enqueue_pipeline(gprb_batch* b, int off, int count, int ngrad, int nr
   GemmArgs ga{b->Lm, b->DinvT, b->Dinv, b->A, b->Lm, b->KinvD, list, ms, dstride, (int)b->npad, J, 0, GEMM_CHOL_DIAG, nv};
   ga.fail = b->fail;
   set_gemm_maps(ga, b);
+  { static const int pf = getenv("GPRB200_PF_CIN") ? atoi(getenv("GPRB200_PF_CIN")) : 1; ga.pf_cin = (!right_looking && pf) ? 1 : 0; }
   if (count > 0) {
   // Small passes are latency bound (one dependent chain of 3 J launches): they use the right-looking factorisation,
   // whose launches are short and wide, instead of the left-looking one, whose k-loops grow with the column index.
@@ -752,6 +753,7 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
     // operand tensor maps of the tile GEMM: padded boxes (132 / 68 rows) x KT columns x one GP
     if ((rc = make_tensor_map(&b->tm_L132, b->Lm, (uint64_t)b->npad, (uint64_t)b->npad, B, (uint64_t)b->npad, mat, NB + 4, KT)) ||
         (rc = make_tensor_map(&b->tm_L68, b->Lm, (uint64_t)b->npad, (uint64_t)b->npad, B, (uint64_t)b->npad, mat, NB / 2 + 4, KT)) ||
+        (rc = make_tensor_map(&b->tm_A68, b->A, (uint64_t)b->npad, (uint64_t)b->npad, B, (uint64_t)b->npad, mat, NB / 2 + 4, KT)) ||
         (rc = make_tensor_map(&b->tm_DT132, b->DinvT, NB, (uint64_t)b->J * NB, B, NB, dinv, NB + 4, KT)) ||
         (rc = make_tensor_map(&b->tm_DT68, b->DinvT, NB, (uint64_t)b->J * NB, B, NB, dinv, NB / 2 + 4, KT)) ||
         (rc = make_tensor_map(&b->tm_D132, b->Dinv, NB, (uint64_t)b->J * NB, B, NB, dinv, NB + 4, KT)))

@@ -174,6 +174,7 @@ struct gprb_batch {
   gprb_predict_slot ps[2];
   // TMA tensor maps of the tile GEMM's operands (encoded once per batch; box = padded rows x KT columns x 1 GP)
   CUtensorMap tm_L132, tm_L68;     // Lm  [B][npad][npad]
+  CUtensorMap tm_A68;              // A   [B][npad][npad] (L2 prefetch of the K tiles the Cholesky modes start from)
   CUtensorMap tm_DT132, tm_DT68;   // DinvT [B][J*128][128]
   CUtensorMap tm_D132;             // Dinv  [B][J*128][128]
   std::vector<cudaEvent_t> gemm_ev;  // profiling: start/stop pairs around every tile-GEMM launch
@@ -232,6 +233,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                    smem_u32(dst)),
                "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                : "memory");
+}
+// The same box, fetched into L2 only (SASS UTMAPF): no shared memory, no barrier, no register - a hint for a later load.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // Order generic-proxy smem writes before later async-proxy (TMA) accesses to the same smem.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

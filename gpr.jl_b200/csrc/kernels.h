@@ -32,7 +32,8 @@ struct GemmArgs {
   const int32_t* fail = nullptr;     // [B] per-GP failure flag: tiles of a GP whose factorisation already broke down exit at once
   unsigned long long* tl = nullptr;  // debug timeline buffer [count][ntiles][8] (only read when built with -DGPRB_TIMELINE)
   // TMA tensor maps of the operands (gprb_batch / gprb_predict_slot own them): box = 132 or 68 padded rows x KT columns
-  CUtensorMap tm_L132, tm_L68, tm_DT132, tm_DT68, tm_D132, tm_T68;
+  CUtensorMap tm_L132, tm_L68, tm_DT132, tm_DT68, tm_D132, tm_T68, tm_A68;
+  int pf_cin = 0;       // 1: Cin is the matrix tm_A68 describes - the CTA prefetches its K half tile into L2 with TMA requests at entry
 };
 
 int launch_tile_gemm(const GemmArgs& g, int ntiles, int count, cudaStream_t stream);

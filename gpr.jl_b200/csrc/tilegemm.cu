@@ -481,6 +481,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_tile_gemm(const __grid_cons
   const int rows_valid = (tc.i == g.J - 1) ? nvl : NB;            // valid output rows of this tile
   // a row half that lies entirely in the padding of the last block row has nothing to compute (uniform over the CTA)
   if (failed != 0 || (!COLSPLIT && hg.r0h >= rows_valid)) return;
+  // The K half tile the accumulators start from is read by per-thread loads in the DMMA accumulator layout: 64-byte pieces,
+  // one DRAM page each.  Eight TMA prefetch requests (64 rows x 16 columns: 512-byte pieces) pull it into L2 first; the
+  // register loads below then merge with / hit those lines.
+  if (!COLSPLIT && g.pf_cin && tc.use_cin && threadIdx.x == 32) {
+#pragma unroll
+    for (int q = 0; q < NB / KT; ++q) tma_prefetch_3d(&g.tm_A68, tc.i * NB + hg.r0h, tc.j * NB + q * KT, gp);
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], N_CONSUMER_WARPS); }
