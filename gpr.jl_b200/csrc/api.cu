@@ -786,7 +786,10 @@ int gprb_batch_create(gprb_ctx* ctx, int32_t B, gprb_dataset* const* ds, const d
         (e = cudaMemset(b->jitter, 0, sizeof(double) * B)) != cudaSuccess ||
         (e = cudaMemset(b->diag_off, 0, sizeof(double) * B)) != cudaSuccess ||
         (e = cudaMemset(b->ymm, 0, sizeof(double) * b->npad * B)) != cudaSuccess ||  // zero padding, written once
-        (e = cudaMemset(b->fail, 0, sizeof(int32_t) * B)) != cudaSuccess) {
+        (e = cudaMemset(b->fail, 0, sizeof(int32_t) * B)) != cudaSuccess ||
+        // k_diag_factor only writes the triangular halves of the inverted diagonal blocks: the zero halves are set here
+        (e = cudaMemset(b->Dinv, 0, sizeof(double) * dinv * B)) != cudaSuccess ||
+        (e = cudaMemset(b->DinvT, 0, sizeof(double) * dinv * B)) != cudaSuccess) {
       rc = cuda_fail(e, "batch init copies", __FILE__, __LINE__);
       break;
     }

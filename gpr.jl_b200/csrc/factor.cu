@@ -275,23 +275,24 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) k_diag_factor(DiagArgs g) {
   // ================= write-out: W = inv(L_jj) column-major into Dinv, its transpose into DinvT =================
   double* Dinv = g.Dinv + (int64_t)gp * g.dinv_stride + (int64_t)j * NB * NB;
   double* DinvT = g.DinvT + (int64_t)gp * g.dinv_stride + (int64_t)j * NB * NB;
+  // Only the ten lower sub-blocks of W (and the ten upper ones of W^T) are written: the other halves of both buffers are
+  // structural zeros, set once when the batch is created and never touched again.
 #pragma unroll 4
-  for (int idx = tid; idx < NB * NB / 2; idx += DIAG_THREADS) {  // (row pair, column) of the 128x128 outputs
-    const int r = 2 * (idx & 63), c = idx >> 6;
-    const int br = r / SB, bc = c / SB, rr = r & (SB - 1), cc = c & (SB - 1);
-    double2 w = make_double2(0.0, 0.0), wt = make_double2(0.0, 0.0);
-    if (br > bc) {          // W(r,c), W(r+1,c) from the row-major slot (br,bc)
-      const double* P = S + slot_of(br, bc);
-      w = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
-    } else if (br == bc) {  // diagonal slot, column-major: W(r..r+1, c) and W^T(r..r+1, c) = W(c, r..r+1)
-      const double* P = S + slot_of(br, br);
-      w = *reinterpret_cast<const double2*>(&P[cc * LDW + rr]);
-      wt = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
-    } else {                // W^T(r,c) = W(c,r), W(c,r+1) from the row-major slot (bc,br)
-      wt = *reinterpret_cast<const double2*>(&S[slot_of(bc, br) + cc * LDW + rr]);
+  for (int idx = tid; idx < NSLOT * SB * SB / 2; idx += DIAG_THREADS) {  // (slot, row pair, column)
+    const int q = idx >> 9, w = idx & 511;
+    const int bi = q < 1 ? 0 : q < 3 ? 1 : q < 6 ? 2 : 3, bj = q - bi * (bi + 1) / 2;
+    const int rr = 2 * (w & 15), cc = w >> 4;
+    const double* P = S + q * SBLK;
+    double2 v, vt;  // v = W(bi*32 + rr .. +1, bj*32 + cc);  vt = W^T(bj*32 + rr .. +1, bi*32 + cc) = W(bi*32 + cc, bj*32 + rr .. +1)
+    if (bi == bj) {  // column-major slot
+      v = *reinterpret_cast<const double2*>(&P[cc * LDW + rr]);
+      vt = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
+    } else {         // row-major slot: W(r,c) at [r*LDW + c]
+      v = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
+      vt = *reinterpret_cast<const double2*>(&P[cc * LDW + rr]);
     }
-    *reinterpret_cast<double2*>(&Dinv[r + c * NB]) = w;
-    *reinterpret_cast<double2*>(&DinvT[r + c * NB]) = wt;
+    *reinterpret_cast<double2*>(&Dinv[(bi * SB + rr) + (bj * SB + cc) * NB]) = v;
+    *reinterpret_cast<double2*>(&DinvT[(bj * SB + rr) + (bi * SB + cc) * NB]) = vt;
   }
   if (warp == 0) {
 #pragma unroll

@@ -257,6 +257,7 @@ def test_optimize_per_gp_virtual_time_limit(gprb):
     from gpr_jl_b200 import data
     from oracle.lbfgs_oracle import LBFGSOptions, lbfgs
     tr = data.make_trial("P1", 96, seed=17)
+    tr = {"X": tr["X"], "Y": tr["Y"] + 0.05 * np.random.default_rng(96).standard_normal(tr["Y"].shape)}  # well-conditioned optimum, see test_optimize_matches_scalar_oracle
     th = data.theta0("P1", tr["X"])
     gps = [gprb.GPE(tr["X"], tr["Y"][k], gprb.MeanZero(), gprb.SEArd(th[1:-1], th[-1]), logNoise=th[0]) for k in range(3)]
     batch = gprb.GPBatch(gps)

@@ -457,6 +457,10 @@ def test_optimize_matches_scalar_oracle(gprb):
     deterministic iteration cap (the reference's time_limit is wall-clock)."""
     from gpr_jl_b200 import data
     tr = data.make_trial("P1", 96, seed=17)
+    # 0.05 N(0,1) of observation noise on the targets: on the generator's nearly noise-free data the optimiser drives
+    # logNoise to -6.5 within 12 iterations (cond(K) ~ 1e8), where a last-bit difference in the factorisation can flip a
+    # backtracking decision and the two trajectories part ways - the comparison would then test luck, not parity
+    tr = {"X": tr["X"], "Y": tr["Y"] + 0.05 * np.random.default_rng(96).standard_normal(tr["Y"].shape)}
     th = data.theta0("P1", tr["X"])
     thetas = np.tile(th, (3, 1))
     batch = build_batch(gprb, [tr], [thetas])
