@@ -187,16 +187,23 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(PredictArgs g) {
 constexpr int PC_THREADS = 256;
 
 // grid (J, B): CTA = 128 training rows x one chunk of <= 128 test columns of one GP.
-// lane -> test column (4 groups of 32), warp -> training row; T row r is written contiguously over the columns.
+// Work unit of a warp = 32 training rows (one per lane) x 8 test columns; ceil(mc / 8) column groups x 4 row blocks per CTA,
+// dealt round-robin over the 8 warps (m = 100, the reference's rollout batch: 52 units, 6.5 per warp, 104 of 104 columns
+// useful - the lane-per-column layout this replaces computed 128).  Per input dimension a unit costs one conflict-free
+// 8-byte load (its row), four broadcast 16-byte loads (the 8 columns) and 16 FP64 instructions, so the FP64 pipe, not the
+// shared-memory crossbar, is the limit (the old layout issued one load per 3 FP64 instructions and was crossbar bound).
+// Inputs are scaled and centred once in shared memory, z = sqrt(w) (x - x_0) with x_0 the GP's first training sample
+// (like k_assemble_gram): r2 = sum (z_i - z_j)^2 is 2 FP64 instructions per pair and dimension instead of 3.
 template <int KIND>
 __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int d = g.d;
   double* Xi = reinterpret_cast<double*>(smem_raw);  // [d][NB]   training tile, one row per input dimension
   double* xsT = Xi + d * NB;                          // [d][PT]   test columns, transposed, zero padded
-  double* w = xsT + d * PT;                           // [MAX_D]
-  double* red = w + MAX_D;                            // [8][PT]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 8 * PT);
+  double* sw = xsT + d * PT;                          // [MAX_D]   sqrt(w_p)
+  double* x0 = sw + MAX_D;                            // [MAX_D]   centre
+  double* red = x0 + MAX_D;                           // [4][PT]   mean partials per row block
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 4 * PT);
   const int gl = blockIdx.y, gp = g.gp_off + gl, ib = blockIdx.x;
   if (g.mask && g.mask[gp] != 0) return;  // no evaluated state: k_predict_finish reports NaN
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -211,50 +218,78 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
     if (uwarp < 4 && lane == 0)
       for (int p = uwarp; p < d; p += 4) bulk_g2s(Xi + p * NB, Xt + (int64_t)p * g.npad + (int64_t)ib * NB, NB * sizeof(double), bar);
   }
-  const double* Xstar = g.Xstar + (int64_t)(gl / g.gpb) * g.xstar_stride + (int64_t)g.s0 * d;
-  for (int idx = threadIdx.x; idx < d * PT; idx += PC_THREADS) {
-    const int s = idx / d, p = idx - s * d;  // consecutive threads walk one test column: coalesced global reads
-    xsT[p * PT + s] = s < g.mc ? Xstar[(int64_t)s * d + p] : 0.0;
+  if (threadIdx.x < d) {
+    sw[threadIdx.x] = sqrt(exp(-2.0 * th[1 + threadIdx.x]));
+    x0[threadIdx.x] = Xt[(int64_t)threadIdx.x * g.npad];
   }
-  if (threadIdx.x < d) w[threadIdx.x] = exp(-2.0 * th[1 + threadIdx.x]);
+  __syncthreads();
+  const int ncg = (g.mc + 7) >> 3;  // column groups of 8
+  const double* Xstar = g.Xstar + (int64_t)(gl / g.gpb) * g.xstar_stride + (int64_t)g.s0 * d;
+  for (int idx = threadIdx.x; idx < d * 8 * ncg; idx += PC_THREADS) {
+    const int s = idx / d, p = idx - s * d;  // consecutive threads walk one test column: coalesced global reads
+    xsT[p * PT + s] = s < g.mc ? sw[p] * (Xstar[(int64_t)s * d + p] - x0[p]) : 0.0;
+  }
   mbar_wait(bar, 0);
+  for (int k = threadIdx.x; k < d * NB; k += PC_THREADS) {
+    const int p = k >> 7;
+    Xi[k] = sw[p] * (Xi[k] - x0[p]);
+  }
   __syncthreads();
   const double sf2 = exp(2.0 * th[d + 1]);
   const double* alpha = g.alpha + (int64_t)gp * g.npad;
-  const int nq = (g.mc + 31) / 32;  // active 32-column groups
-  double macc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int rl = warp; rl < NB; rl += PC_THREADS / 32) {
-    const int r = ib * NB + rl;
-    double r2[4] = {0.0, 0.0, 0.0, 0.0};
-    if (r < g.n) {
-      for (int p = 0; p < d; ++p) {
-        const double xv = Xi[p * NB + rl], wp = w[p];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  for (int u = warp; u < 4 * ncg; u += PC_THREADS / 32) {
+    const int cg = u >> 2, rb = u & 3, rl = rb * 32 + lane, r = ib * NB + rl;
+    double r2[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q < nq) {
-            const double df = xv - xsT[p * PT + lane + 32 * q];
-            r2[q] = fma(wp, df * df, r2[q]);
-          }
+    for (int k = 0; k < 8; ++k) r2[k] = 0.0;
+    const double* xr = Xi + rl;
+    const double* xc = xsT + 8 * cg;
+#pragma unroll 2
+    for (int p = 0; p < d; ++p) {
+      const double xv = xr[p * NB];
+      const double2* cp = reinterpret_cast<const double2*>(xc + p * PT);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double2 c = cp[k];
+        const double d0 = xv - c.x, d1 = xv - c.y;
+        r2[2 * k] = fma(d0, d0, r2[2 * k]);
+        r2[2 * k + 1] = fma(d1, d1, r2[2 * k + 1]);
       }
     }
-    const double ar = r < g.n ? alpha[r] : 0.0;
+    const bool rok = r < g.n;
+    const double ar = rok ? alpha[r] : 0.0;
+    double v[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int s = lane + 32 * q;
-      const double kv = (r < g.n && s < g.mc) ? kcross<KIND>(r2[q], sf2) : 0.0;
-      if (g.T) g.T[((int64_t)gl * g.npad + r) * PT + s] = kv;
-      macc[q] = fma(kv, ar, macc[q]);
+    for (int k = 0; k < 8; ++k) v[k] = (rok && 8 * cg + k < g.mc) ? kcross<KIND>(r2[k], sf2) : 0.0;
+    if (g.T) {
+      double2* tp = reinterpret_cast<double2*>(g.T + ((int64_t)gl * g.npad + r) * PT + 8 * cg);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tp[k] = make_double2(v[2 * k], v[2 * k + 1]);
     }
-  }
+    // mean partials: sum over the 32 rows of v[k] alpha_r for the 8 columns - a transposing butterfly (4 + 2 + 1 exchanges
+    // halve the values a lane carries, two more finish the sum): 9 shuffles instead of 40, fixed order
 #pragma unroll
-  for (int q = 0; q < 4; ++q) red[warp * PT + lane + 32 * q] = macc[q];
+    for (int k = 0; k < 8; ++k) v[k] *= ar;
+    double a4[4], a2[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double send = b4 ? v[k] : v[k + 4], keep = b4 ? v[k + 4] : v[k];
+      a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double send = b3 ? a4[k] : a4[k + 2], keep = b3 ? a4[k + 2] : a4[k];
+      a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    double a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    if ((lane & 3) == 0) red[rb * PT + 8 * cg + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = a1;
+  }
   __syncthreads();
-  if (threadIdx.x < PT) {
-    double sum = 0.0;
-#pragma unroll
-    for (int k = 0; k < PC_THREADS / 32; ++k) sum += red[k * PT + threadIdx.x];
-    g.mupart[((int64_t)gl * g.J + ib) * PT + threadIdx.x] = sum;
-  }
+  if ((int)threadIdx.x < 8 * ncg)
+    g.mupart[((int64_t)gl * g.J + ib) * PT + threadIdx.x] = (red[threadIdx.x] + red[PT + threadIdx.x]) + (red[2 * PT + threadIdx.x] + red[3 * PT + threadIdx.x]);
 }
 
 // grid B, 512 threads: thread = (row partition, test column).  mu = sum of the block partials + m(x*);
@@ -299,7 +334,7 @@ __global__ void __launch_bounds__(512) k_predict_finish(PredictTileArgs g) {
 int launch_predict_cross(const PredictTileArgs& a, int count, cudaStream_t stream) {
   const int B = count;
   if (B <= 0 || a.mc <= 0) return 0;
-  const size_t smem = ((size_t)a.d * NB + (size_t)a.d * PT + MAX_D + 8 * PT) * sizeof(double) + 16;
+  const size_t smem = ((size_t)a.d * NB + (size_t)a.d * PT + 2 * MAX_D + 4 * PT) * sizeof(double) + 16;
   dim3 grid(a.J, B);
   cudaError_t e;
 #define GPRB_PC_CASE(K)                                                                                       \
