@@ -994,6 +994,7 @@ static int predict_enqueue(gprb_batch* b, int slot, int gp0, int gp1, int64_t m,
       ta.gp_off = gp0;
       ta.mask = sl.mask;
       ta.gpb = gpb;
+      { static const char* ev = getenv("GPRB200_PC_ZMAX"); if (ev) ta.zmax = atof(ev); }
       if ((rc = launch_predict_cross(ta, count, st))) return rc;
       b->ctx->launches++;
       if (want_var) {

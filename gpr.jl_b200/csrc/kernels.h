@@ -155,6 +155,7 @@ struct PredictTileArgs {
   int gp_off = 0;           // first GP of the range (local index = gp - gp_off, see PredictArgs)
   const int32_t* mask = nullptr;  // [B] or nullptr
   int gpb = 1;              // consecutive GPs sharing one Xstar block (see PredictArgs)
+  double zmax = 1.0e3;      // largest scaled, centred input coordinate k_predict_cross uses its 2-instruction distance form for
 };
 int launch_predict_cross(const PredictTileArgs& a, int count, cudaStream_t stream);
 int launch_predict_finish(const PredictTileArgs& a, int count, cudaStream_t stream);

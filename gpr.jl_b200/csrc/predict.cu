@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
   double* xsT = Xi + d * NB;                          // [d][PT]   test columns, transposed, zero padded
   double* sw = xsT + d * PT;                          // [MAX_D]   sqrt(w_p)
   double* x0 = sw + MAX_D;                            // [MAX_D]   centre
-  double* red = x0 + MAX_D;                           // [4][PT]   mean partials per row block
+  double* wv = x0 + MAX_D;                            // [MAX_D]   w_p
+  double* red = wv + MAX_D;                           // [4][PT]   mean partials per row block
   uint64_t* bar = reinterpret_cast<uint64_t*>(red + 4 * PT);
   const int gl = blockIdx.y, gp = g.gp_off + gl, ib = blockIdx.x;
   if (g.mask && g.mask[gp] != 0) return;  // no evaluated state: k_predict_finish reports NaN
@@ -218,23 +219,43 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
     if (uwarp < 4 && lane == 0)
       for (int p = uwarp; p < d; p += 4) bulk_g2s(Xi + p * NB, Xt + (int64_t)p * g.npad + (int64_t)ib * NB, NB * sizeof(double), bar);
   }
+  __shared__ unsigned long long zmax_bits;  // max |z| over the tile and the test columns (bit pattern: non-negative doubles order like integers)
   if (threadIdx.x < d) {
-    sw[threadIdx.x] = sqrt(exp(-2.0 * th[1 + threadIdx.x]));
+    const double wp = exp(-2.0 * th[1 + threadIdx.x]);
+    sw[threadIdx.x] = sqrt(wp);
+    wv[threadIdx.x] = wp;
     x0[threadIdx.x] = Xt[(int64_t)threadIdx.x * g.npad];
   }
+  if (threadIdx.x == 0) zmax_bits = 0ull;
   __syncthreads();
   const int ncg = (g.mc + 7) >> 3;  // column groups of 8
   const double* Xstar = g.Xstar + (int64_t)(gl / g.gpb) * g.xstar_stride + (int64_t)g.s0 * d;
+  double zm = 0.0;
   for (int idx = threadIdx.x; idx < d * 8 * ncg; idx += PC_THREADS) {
     const int s = idx / d, p = idx - s * d;  // consecutive threads walk one test column: coalesced global reads
-    xsT[p * PT + s] = s < g.mc ? sw[p] * (Xstar[(int64_t)s * d + p] - x0[p]) : 0.0;
+    const double xv = s < g.mc ? Xstar[(int64_t)s * d + p] : x0[p];
+    xsT[p * PT + s] = xv;
+    zm = fmax(zm, fabs(sw[p] * (xv - x0[p])));
   }
   mbar_wait(bar, 0);
-  for (int k = threadIdx.x; k < d * NB; k += PC_THREADS) {
-    const int p = k >> 7;
-    Xi[k] = sw[p] * (Xi[k] - x0[p]);
-  }
+  for (int k = threadIdx.x; k < d * NB; k += PC_THREADS) zm = fmax(zm, fabs(sw[k >> 7] * (Xi[k] - x0[k >> 7])));
+  if (!(zm <= g.zmax)) zm = 1.0e300;  // (also NaN / Inf inputs) -> the unscaled path
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) zm = fmax(zm, __shfl_xor_sync(0xffffffffu, zm, off));
+  if (lane == 0) atomicMax(&zmax_bits, (unsigned long long)__double_as_longlong(zm));
   __syncthreads();
+  // Scaled path: z = sqrt(w)(x - x_0) rounds every coordinate once, an absolute error of eps |z| in z_i - z_j and so a
+  // relative error of <= ~2 eps |z| |z_i - z_j| in K (entries that matter have |z_i - z_j| < 40): below 2e-11 for
+  // |z| <= zmax = 1e3.  Extreme length-scales (config.json has l down to 1e-4) keep the raw inputs and the 3-instruction form.
+  const bool scaled = __longlong_as_double((long long)zmax_bits) <= g.zmax;
+  if (scaled) {
+    for (int idx = threadIdx.x; idx < d * 8 * ncg; idx += PC_THREADS) {
+      const int s = idx / d, p = idx - s * d;
+      xsT[p * PT + s] = sw[p] * (xsT[p * PT + s] - x0[p]);
+    }
+    for (int k = threadIdx.x; k < d * NB; k += PC_THREADS) Xi[k] = sw[k >> 7] * (Xi[k] - x0[k >> 7]);
+    __syncthreads();
+  }
   const double sf2 = exp(2.0 * th[d + 1]);
   const double* alpha = g.alpha + (int64_t)gp * g.npad;
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
@@ -245,16 +266,30 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
     for (int k = 0; k < 8; ++k) r2[k] = 0.0;
     const double* xr = Xi + rl;
     const double* xc = xsT + 8 * cg;
+    if (scaled) {
 #pragma unroll 2
-    for (int p = 0; p < d; ++p) {
-      const double xv = xr[p * NB];
-      const double2* cp = reinterpret_cast<const double2*>(xc + p * PT);
+      for (int p = 0; p < d; ++p) {
+        const double xv = xr[p * NB];
+        const double2* cp = reinterpret_cast<const double2*>(xc + p * PT);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double2 c = cp[k];
-        const double d0 = xv - c.x, d1 = xv - c.y;
-        r2[2 * k] = fma(d0, d0, r2[2 * k]);
-        r2[2 * k + 1] = fma(d1, d1, r2[2 * k + 1]);
+        for (int k = 0; k < 4; ++k) {
+          const double2 c = cp[k];
+          const double d0 = xv - c.x, d1 = xv - c.y;
+          r2[2 * k] = fma(d0, d0, r2[2 * k]);
+          r2[2 * k + 1] = fma(d1, d1, r2[2 * k + 1]);
+        }
+      }
+    } else {
+      for (int p = 0; p < d; ++p) {
+        const double xv = xr[p * NB], wp = wv[p];
+        const double2* cp = reinterpret_cast<const double2*>(xc + p * PT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double2 c = cp[k];
+          const double d0 = xv - c.x, d1 = xv - c.y;
+          r2[2 * k] = fma(wp, d0 * d0, r2[2 * k]);
+          r2[2 * k + 1] = fma(wp, d1 * d1, r2[2 * k + 1]);
+        }
       }
     }
     const bool rok = r < g.n;
@@ -334,7 +369,7 @@ __global__ void __launch_bounds__(512) k_predict_finish(PredictTileArgs g) {
 int launch_predict_cross(const PredictTileArgs& a, int count, cudaStream_t stream) {
   const int B = count;
   if (B <= 0 || a.mc <= 0) return 0;
-  const size_t smem = ((size_t)a.d * NB + (size_t)a.d * PT + 2 * MAX_D + 4 * PT) * sizeof(double) + 16;
+  const size_t smem = ((size_t)a.d * NB + (size_t)a.d * PT + 3 * MAX_D + 4 * PT) * sizeof(double) + 16;
   dim3 grid(a.J, B);
   cudaError_t e;
 #define GPRB_PC_CASE(K)                                                                                       \

@@ -603,3 +603,28 @@ def test_batched_experiment_equals_per_gp_reference_sequence(gprb):
                 mu = np.array([gprb.predict_y(gp, obs)[0][0] for gp in gps])
                 state = step_fn(t, obs, mu[:, None])[:, 0]
             np.testing.assert_allclose(final[t][:, s], state, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("ell,m", [(1.0, 100), (1e-4, 100), (1e-4, 3)])
+def test_predict_cross_covariance_extreme_length_scale(gprb, ell, m):
+    """k_predict_cross measures distances on inputs scaled by sqrt(w) and centred at the first training sample (two FP64
+    instructions per pair and dimension); when a scaled coordinate exceeds 1e3 - length-scales down to 1e-4 are in the
+    reference's config.json - it keeps the raw inputs and the three-instruction form.  Test points sit a fraction of a
+    length-scale away from training points, far from the centre, so both forms are exercised on entries that matter."""
+    rng = np.random.default_rng(int(-np.log10(ell)) * 10 + m)
+    n, d = 200, 3
+    X = np.asfortranarray(rng.uniform(-2.0, 2.0, (d, n)))
+    y = np.sin(X[0]) + 0.1 * rng.standard_normal(n)
+    th = np.array([-2.0, np.log(ell), np.log(1.5 * ell), np.log(0.7 * ell), 0.3])
+    Xs = np.asfortranarray(X[:, rng.integers(0, n, m)] + 0.3 * ell * rng.standard_normal((d, m)))
+    gp = gprb.GPE(X, y, gprb.MeanZero(), gprb.SEArd(th[1:-1].copy(), th[-1]), logNoise=th[0])
+    batch = gprb.GPBatch([gp])
+    batch.eval(grad=False)
+    mu, var = batch.predict_y(Xs)
+    Xr = np.ascontiguousarray(X.T)
+    r = go.eval_mll(Xr, y, th, with_grad=False, return_state=True)
+    m_o, v_o = go.predict(Xr, th, r["state"], np.ascontiguousarray(Xs.T))
+    assert np.abs(m_o).max() > 1e-2  # the test points do see their training neighbours
+    assert rel(mu[0], m_o) <= 1e-9
+    np.testing.assert_allclose(var[0], v_o, rtol=1e-9, atol=1e-13)
+    batch.close()
