@@ -207,6 +207,9 @@ def main():
                     help="BASELINE config family (default CP, the one the metric is quoted on); FB = d=52, 12 GPs per trial")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-predict", action="store_true")
+    ap.add_argument("--split", default="trial", choices=["trial", "gp"],
+                    help="strong scaling only - trial (default): trial t on rank t mod world, the reference's jobid axis; gp: the "
+                         "T*G GPs cut into equal contiguous ranges (a trial may straddle two ranks, both upload its X)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, what the driver runs): every rank owns --trials trials; strong: the SAME --trials "
                          "trials (north_star: '100 trial datasets batched across 8xB200') are split round-robin over the ranks")
@@ -232,7 +235,17 @@ def main():
 
     from gpr_jl_b200 import shard
     n = args.n
-    if args.scaling == "strong":  # the same T trials for every world size, trial t on rank t mod world (core.jl:28's jobid axis)
+    G_cfg = len(data.SYSTEMS[data.CONFIGS[args.system]["system"]]["outputs"])
+    if args.scaling == "strong" and args.split == "gp":  # equal GP ranges: (trial, output) units, X of a straddling trial on both ranks
+        units = shard.gps_for_rank(args.trials, G_cfg, rank, world)
+        trials, mine = [], []
+        for (t, g0, g1) in units:
+            tr = data.make_config(args.system, trials=1, n=n, first_trial=t)[0]
+            tr["Y"], tr["theta0"] = tr["Y"][g0:g1], tr["theta0"][g0:g1]
+            trials.append(tr)
+            mine.append((t, g0, g1))
+        T_total = args.trials
+    elif args.scaling == "strong":  # the same T trials for every world size, trial t on rank t mod world (core.jl:28's jobid axis)
         mine = shard.trials_for_rank(args.trials, rank, world)
         trials = [data.make_config(args.system, trials=1, n=n, first_trial=t)[0] for t in mine]
         T_total = args.trials
@@ -241,7 +254,7 @@ def main():
         mine = [rank * args.trials + t for t in range(args.trials)]
         T_total = world * args.trials
     T = len(trials)
-    G_out = trials[0]["Y"].shape[0]
+    G_out = G_cfg
     d = trials[0]["X"].shape[0]
     gps = []
     for tr in trials:
@@ -260,7 +273,8 @@ def main():
     mll_dev = torch.empty(B, dtype=torch.float64, device=dev)
     grad_dev = torch.empty(B, P, dtype=torch.float64, device=dev)
     info_dev = torch.empty(B, dtype=torch.int32, device=dev)
-    Bmax = -(-args.trials // world) * G_out if args.scaling == "strong" else B  # padded per-rank rows of the device gather
+    # padded per-rank rows of the device gather
+    Bmax = (-(-args.trials * G_out // world) if args.split == "gp" else -(-args.trials // world) * G_out) if args.scaling == "strong" else B
     gathered = [torch.empty(Bmax, P + 1, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
     send = torch.zeros(Bmax, P + 1, dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream()
@@ -332,9 +346,17 @@ def main():
         t_b = time.perf_counter()
         out = batch.eval(theta=thetas[i], grad=True)
         if world > 1:  # the path's one collective: per-trial result rows to every rank (gprb_gather: ncclAllGather in the .so)
-            rows = {mine[t]: np.concatenate([out[0][t * G_out:(t + 1) * G_out], out[1][t * G_out:(t + 1) * G_out].ravel()])
-                    for t in range(T)}
-            ctx.gather(rows, T_total, G_out * (P + 1))
+            if args.scaling == "strong" and args.split == "gp":  # one row per GP, keyed by its global index
+                rows, k = {}, 0
+                for (t, g0, g1) in mine:
+                    for g in range(g0, g1):
+                        rows[t * G_out + g] = np.concatenate([out[0][k:k + 1], out[1][k]])
+                        k += 1
+                ctx.gather(rows, T_total * G_out, P + 1)
+            else:
+                rows = {mine[t]: np.concatenate([out[0][t * G_out:(t + 1) * G_out], out[1][t * G_out:(t + 1) * G_out].ravel()])
+                        for t in range(T)}
+                ctx.gather(rows, T_total, G_out * (P + 1))
         host_ms[0] += (t_b - t_a) * 1e3
         host_ms[1] += (time.perf_counter() - t_b) * 1e3
         return out
@@ -350,6 +372,8 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = B_total * args.steps / float(dt.item())
     h2d = T_total * d * n * 8 + B_total * n * 8 + B_total * P * 8  # whole job: X, y - m, theta of every GP, every step
+    if args.scaling == "strong" and args.split == "gp":  # X of a trial that straddles two ranks goes up twice
+        h2d += (world - 1 - sum(1 for r in range(1, world) if (T_total * G_out * r // world) % G_out == 0)) * d * n * 8
     d2h = B_total * 8 + B_total * P * 8 + B_total * 4
 
     # ---- prediction throughput (second half of the BASELINE metric): 100 test states per GP (the 100 test states of a
@@ -433,7 +457,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{WORKLOAD_NAMES[args.system]}, n={n}, d={d}, G={G_out} GPs/trial, {args.trials} trials (B={args.trials * G_out} GPs per GPU)"
                                    if args.scaling == "weak" else
-                                   f"{WORKLOAD_NAMES[args.system]}, n={n}, d={d}, G={G_out} GPs/trial, {args.trials} trials in total split over {world} GPUs (B={B} GPs on rank 0)",
+                                   f"{WORKLOAD_NAMES[args.system]}, n={n}, d={d}, G={G_out} GPs/trial, {args.trials} trials in total split over {world} GPUs "
+                                   f"({'equal GP ranges' if args.split == 'gp' else 'trial t on rank t mod N'}; B={B} GPs on rank 0)",
                        "evals_per_step": B_total,
                        "theta": ("config.json CP_MAX2048" if args.system == "CP" else "theta_0 of the config (data.CONFIGS)") + " + 0.1*N(0,I), fresh per step",
                        "l2": f"working set {2 * B * batch.n * batch.n * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",

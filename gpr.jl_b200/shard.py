@@ -25,6 +25,23 @@ def owner_of(trial: int, world: int) -> int:
     return trial % world
 
 
+def gps_for_rank(n_trials: int, outputs_per_trial: int, rank: int, world: int):
+    """Balanced split at GP granularity: the n_trials * G GPs, in trial-major order, are cut into ``world`` contiguous
+    ranges whose sizes differ by at most one.  Returns [(trial, first output, last output + 1), ...] for this rank.
+
+    The G GPs of a trial are independent problems that only share the read-only inputs X, so a trial may straddle two
+    ranks (both upload its X).  With 100 trials on 8 GPUs the trial split gives the busiest rank 13 trials against a mean
+    of 12.5 (4 % imbalance); the GP split gives every rank exactly 50 (CP) / 150 (FB) GPs."""
+    total = n_trials * outputs_per_trial
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    out = []
+    for t in range(lo // outputs_per_trial, (hi + outputs_per_trial - 1) // outputs_per_trial):
+        g0, g1 = max(lo, t * outputs_per_trial) - t * outputs_per_trial, min(hi, (t + 1) * outputs_per_trial) - t * outputs_per_trial
+        if g1 > g0:
+            out.append((t, g0, g1))
+    return out
+
+
 def gather_trial_results(local: dict, n_trials: int, width: int, device=None, ctx=None):
     """All-gather per-trial result rows.  ``ctx``: a gp.context() whose comm_init() ran -> gprb_gather (NCCL inside
     the library); otherwise torch.distributed (gloo on CPU).
