@@ -121,19 +121,32 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) k_diag_factor(DiagArgs g) {
       for (int c = 0; c < SB; ++c) a[c] = D[c * LDW + lane];
       int bad = 0;
       double mydinv = 1.0;  // lane c ends up with 1 / L_cc
+      // Software-pipelined over the columns: as soon as column c + 1 has its update from column c, its pivot is broadcast
+      // and the reciprocal square root started, BEFORE the remaining trailing updates of column c are issued.  The warp
+      // issues in order: with the pivot taken at the top of the next iteration, the ~120-cycle rsqrt could only start
+      // after all 3 (31 - c) update instructions had been issued.  Same operations on the same operands: bit-identical.
+      double piv = __shfl_sync(FULL, a[0], 0);
+      if (!(piv > 0.0)) {  // LAPACK dpotf2 rule: pivot <= 0 or NaN
+        bad = j0 + 1;
+        piv = 1.0;
+      }
+      double inv = rsqrt(piv);
 #pragma unroll
       for (int c = 0; c < SB; ++c) {
-        double piv = __shfl_sync(FULL, a[c], c);
-        if (!(piv > 0.0)) {  // LAPACK dpotf2 rule: pivot <= 0 or NaN
-          if (bad == 0) bad = j0 + c + 1;
-          piv = 1.0;
-        }
-        const double inv = rsqrt(piv);
         const double lrc = (lane == c) ? piv * inv : a[c] * inv;  // L(lane, c), valid for lane >= c
         a[c] = lrc;
         if (lane == c) mydinv = inv;
+        if (c + 1 < SB) {
+          a[c + 1] = fma(-lrc, __shfl_sync(FULL, lrc, c + 1), a[c + 1]);
+          piv = __shfl_sync(FULL, a[c + 1], c + 1);
+          if (!(piv > 0.0)) {
+            if (bad == 0) bad = j0 + c + 2;
+            piv = 1.0;
+          }
+          inv = rsqrt(piv);
 #pragma unroll
-        for (int k = c + 1; k < SB; ++k) a[k] = fma(-lrc, __shfl_sync(FULL, lrc, k), a[k]);  // valid for lane >= k
+          for (int k = c + 2; k < SB; ++k) a[k] = fma(-lrc, __shfl_sync(FULL, lrc, k), a[k]);  // valid for lane >= k
+        }
       }
       if (bad != 0 && lane == 0 && bad_col == 0) bad_col = bad;
       logdet -= log(mydinv);  // log L_cc = -log(1 / L_cc) of this lane's pivot; warp-reduced once at the end of the kernel
