@@ -345,11 +345,17 @@ __global__ void __launch_bounds__(512) k_predict_finish(PredictTileArgs g) {
     }
     return;
   }
-  if (g.var) {
+  if (g.var && s < g.mc) {  // the columns beyond mc of a chunk are never read (k_predict_cross does not write them either)
     const double* T = g.T + (int64_t)gl * g.npad * PT + s;
     const int per = (g.n + 3) / 4, r0 = part * per, r1 = min(g.n, r0 + per);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int r = r0;
+    for (; r + 7 < r1; r += 8) {  // eight loads in flight per thread; every accumulator still sees its rows in the same order
+      const double v0 = T[(int64_t)r * PT], v1 = T[(int64_t)(r + 1) * PT], v2 = T[(int64_t)(r + 2) * PT], v3 = T[(int64_t)(r + 3) * PT];
+      const double v4 = T[(int64_t)(r + 4) * PT], v5 = T[(int64_t)(r + 5) * PT], v6 = T[(int64_t)(r + 6) * PT], v7 = T[(int64_t)(r + 7) * PT];
+      a0 = fma(v0, v0, a0); a1 = fma(v1, v1, a1); a2 = fma(v2, v2, a2); a3 = fma(v3, v3, a3);
+      a0 = fma(v4, v4, a0); a1 = fma(v5, v5, a1); a2 = fma(v6, v6, a2); a3 = fma(v7, v7, a3);
+    }
     for (; r + 3 < r1; r += 4) {
       const double v0 = T[(int64_t)r * PT], v1 = T[(int64_t)(r + 1) * PT], v2 = T[(int64_t)(r + 2) * PT], v3 = T[(int64_t)(r + 3) * PT];
       a0 = fma(v0, v0, a0); a1 = fma(v1, v1, a1); a2 = fma(v2, v2, a2); a3 = fma(v3, v3, a3);
