@@ -32,6 +32,12 @@ def main():
     ap.add_argument("--tests", type=int, default=100, help="test states per trial (examples/noise.jl:62 testsamples)")
     ap.add_argument("--steps", type=int, default=20, help="rollout steps (simsteps)")
     ap.add_argument("--iterations", type=int, default=5)
+    ap.add_argument("--time-limit", type=float, default=0.0,
+                    help="Optim.Options(time_limit=...) per GP on the deterministic virtual clock (CPnoise.jl:41 uses 10 s); 0 = off")
+    ap.add_argument("--cost-value", type=float, default=1.3, help="virtual seconds charged per value-only evaluation")
+    ap.add_argument("--cost-grad", type=float, default=3.3, help="virtual seconds charged per value+gradient evaluation "
+                    "(defaults: one host core of the bench box at n = 2000, from the cpu_baseline of bench.py)")
+    ap.add_argument("--theta-key", default=None, help="start point from the reference's config.json entry (e.g. CP_MAX2048) instead of the rule")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -50,9 +56,14 @@ def main():
     trials = [data.make_trial(a.system, a.n, seed=9000 + t, n_test=a.tests) for t in mine]
     # one shared start point for every GP, like the reference's config.json entry: derived from trial 0 on every rank
     ref_X = data.make_trial(a.system, a.n, seed=9000)["X"]
-    params = np.exp(np.concatenate([[0.0], data.theta0(a.system, ref_X)[1:-1]]))  # config.json order [s_f, l...]
+    th0 = data.theta0(a.system, ref_X, a.theta_key)
+    params = np.exp(np.concatenate([[th0[-1]], th0[1:-1]]))  # config.json order [s_f, l...]
     t0 = time.perf_counter()
-    batch, res = experiment.fit_trials(trials, params, options=G.Options(iterations=a.iterations))
+    if a.time_limit > 0:  # the reference's stopping rule: a per-GP time budget, here on a virtual clock
+        opts = G.Options(iterations=1000, time_limit=a.time_limit, cost_value=a.cost_value, cost_grad=a.cost_grad)
+    else:
+        opts = G.Options(iterations=a.iterations)
+    batch, res = experiment.fit_trials(trials, params, options=opts)
     t_fit = time.perf_counter() - t0
     Gout = idx.size
 
@@ -75,7 +86,9 @@ def main():
     table = shard.gather_trial_results(rows, a.trials, Gout * P + 2 * Gout + 1, device=torch.device("cuda", local))
     if rank == 0:
         print(json.dumps({"system": a.system, "trials": a.trials, "n": a.n, "world": world, "gps_per_rank": batch.B,
-                          "fit_seconds": t_fit, "rollout_seconds": t_roll, "rollout_predictions": len(mine) * Gout * a.tests * a.steps,
+                          "fit_seconds": t_fit, "rollout_seconds": t_roll,
+                          "optimizer": {"time_limit_per_gp": a.time_limit, "cost_value": a.cost_value, "cost_grad": a.cost_grad} if a.time_limit > 0 else {"iterations": a.iterations},
+                          "mean_iterations": float(np.mean([r["iterations"] for r in res])), "evaluations": int(sum(r["f_calls"] + r["g_calls"] for r in res)), "rollout_predictions": len(mine) * Gout * a.tests * a.steps,
                           "gathered_rows": int(np.isfinite(table[:, -1]).sum()), "mean_kstep_mse": float(np.mean(table[:, -1])), "mean_mll": float(np.mean(table[:, Gout * P:Gout * P + Gout])),
                           "all_info_ok": bool(np.all(table[:, Gout * P + Gout:Gout * P + 2 * Gout] >= 0))}))
     batch.close()
