@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(PC_THREADS) k_predict_cross(PredictTileArgs g)
     zm = fmax(zm, fabs(sw[p] * (xv - x0[p])));
   }
   mbar_wait(bar, 0);
-  for (int k = threadIdx.x; k < d * NB; k += PC_THREADS) zm = fmax(zm, fabs(sw[k >> 7] * (Xi[k] - x0[k >> 7])));
+  for (int k = threadIdx.x; k < d * NB; k += PC_THREADS)  // valid rows only: the zero padding behind row n is masked below, whatever it scales to
+    if (ib * NB + (k & (NB - 1)) < g.n) zm = fmax(zm, fabs(sw[k >> 7] * (Xi[k] - x0[k >> 7])));
   if (!(zm <= g.zmax)) zm = 1.0e300;  // (also NaN / Inf inputs) -> the unscaled path
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) zm = fmax(zm, __shfl_xor_sync(0xffffffffu, zm, off));
