@@ -290,22 +290,36 @@ __global__ void __launch_bounds__(DIAG_THREADS, 2) k_diag_factor(DiagArgs g) {
   double* DinvT = g.DinvT + (int64_t)gp * g.dinv_stride + (int64_t)j * NB * NB;
   // Only the ten lower sub-blocks of W (and the ten upper ones of W^T) are written: the other halves of both buffers are
   // structural zeros, set once when the batch is created and never touched again.
-#pragma unroll 4
-  for (int idx = tid; idx < NSLOT * SB * SB / 2; idx += DIAG_THREADS) {  // (slot, row pair, column)
-    const int q = idx >> 9, w = idx & 511;
+  // A thread transposes 2x2 entries: two 16-byte shared-memory loads along the slot's contiguous direction give it
+  // W(r..r+1, c..c+1), which is one 16-byte store per output column of W and one per output row of W^T.  The lane layout
+  // (4 pairs along the contiguous direction x 8 pairs across it) keeps the loads conflict-free with the 36-double pitch;
+  // reading row pairs of a row-major slot with scalar loads, as a column-major output order suggests, was an 8-way conflict.
+  for (int pc = warp; pc < NSLOT * 8; pc += DIAG_THREADS / 32) {  // 8 pieces of 16 x 8 (or 8 x 16) entries per slot
+    const int q = pc >> 3, sub = pc & 7;
     const int bi = q < 1 ? 0 : q < 3 ? 1 : q < 6 ? 2 : 3, bj = q - bi * (bi + 1) / 2;
-    const int rr = 2 * (w & 15), cc = w >> 4;
     const double* P = S + q * SBLK;
-    double2 v, vt;  // v = W(bi*32 + rr .. +1, bj*32 + cc);  vt = W^T(bj*32 + rr .. +1, bi*32 + cc) = W(bi*32 + cc, bj*32 + rr .. +1)
-    if (bi == bj) {  // column-major slot
-      v = *reinterpret_cast<const double2*>(&P[cc * LDW + rr]);
-      vt = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
-    } else {         // row-major slot: W(r,c) at [r*LDW + c]
-      v = make_double2(P[rr * LDW + cc], P[(rr + 1) * LDW + cc]);
-      vt = *reinterpret_cast<const double2*>(&P[cc * LDW + rr]);
+    double2 w0, w1, t0, t1;  // w0 / w1 = W(r..r+1, c) / W(r..r+1, c+1);  t0 / t1 = W(r, c..c+1) / W(r+1, c..c+1)
+    int rr, cc;
+    if (bi == bj) {  // column-major slot, W(r,c) at [c*LDW + r]: lanes 4 row pairs x 8 column pairs, piece = 8 rows x 16 columns
+      rr = (sub & 3) * 8 + 2 * (lane & 3);
+      cc = (sub >> 2) * 16 + 2 * (lane >> 2);
+      w0 = *reinterpret_cast<const double2*>(&P[cc * LDW + rr]);
+      w1 = *reinterpret_cast<const double2*>(&P[(cc + 1) * LDW + rr]);
+      t0 = make_double2(w0.x, w1.x);
+      t1 = make_double2(w0.y, w1.y);
+    } else {         // row-major slot, W(r,c) at [r*LDW + c]: lanes 4 column pairs x 8 row pairs, piece = 16 rows x 8 columns
+      cc = (sub & 3) * 8 + 2 * (lane & 3);
+      rr = (sub >> 2) * 16 + 2 * (lane >> 2);
+      t0 = *reinterpret_cast<const double2*>(&P[rr * LDW + cc]);
+      t1 = *reinterpret_cast<const double2*>(&P[(rr + 1) * LDW + cc]);
+      w0 = make_double2(t0.x, t1.x);
+      w1 = make_double2(t0.y, t1.y);
     }
-    *reinterpret_cast<double2*>(&Dinv[(bi * SB + rr) + (bj * SB + cc) * NB]) = v;
-    *reinterpret_cast<double2*>(&DinvT[(bj * SB + rr) + (bi * SB + cc) * NB]) = vt;
+    const int r = bi * SB + rr, c = bj * SB + cc;
+    *reinterpret_cast<double2*>(&Dinv[r + c * NB]) = w0;
+    *reinterpret_cast<double2*>(&Dinv[r + (c + 1) * NB]) = w1;
+    *reinterpret_cast<double2*>(&DinvT[c + r * NB]) = t0;
+    *reinterpret_cast<double2*>(&DinvT[c + (r + 1) * NB]) = t1;
   }
   if (warp == 0) {
 #pragma unroll
